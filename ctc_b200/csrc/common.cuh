@@ -1,0 +1,96 @@
+// Shared helpers for the nbctc CUDA translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "nbctc.h"
+
+namespace nbctc {
+
+// ---- error plumbing (thread-local message; nothing crosses the ABI but an int) -------
+void set_error(const char* fmt, ...);
+void clear_error();
+extern std::atomic<uint64_t> g_launch_count;
+
+#define NBCTC_CUDA_CHECK(expr)                                                          \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::nbctc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NBCTC_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+#define NBCTC_LAUNCH_CHECK()                                                            \
+  do {                                                                                  \
+    ::nbctc::g_launch_count.fetch_add(1, std::memory_order_relaxed);                    \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::nbctc::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NBCTC_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+// ---- problem description handed to the kernels ---------------------------------------
+struct Problem {
+  const float* logits;       // (T,B,C)
+  const int32_t* labels;     // (B,Lmax)            [single-label variant]
+  const float* targets;      // (B,Lmax,C)          [binary variant]
+  const int64_t* in_len;     // (B)
+  const int64_t* tgt_len;    // (B)
+  float* loss;               // (B)
+  double* loss_sum;          // scalar or null: sum_b loss[b] (float64, fixed order)
+  float* loss_reduced;       // scalar or null: w_scalar * sum_b seq_w[b] * loss[b]
+  float* grad;               // (T,B,C) or null
+  const float* seq_w;        // (B) or null
+  float w_scalar;
+  int64_t T, B, C, Lmax;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// generic (unfused) path
+size_t generic_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// fused path (single kernel: row stream -> alpha, beta -> gradient)
+bool fused_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary);
+size_t fused_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary);
+int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// deterministic reduction of the per-sequence losses (float64, fixed order)
+int reduce_loss_launch(const Problem& p, cudaStream_t stream);
+
+#ifdef __CUDACC__
+// ---- device helpers ------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// log(exp(a)+exp(b)) in float64, -inf safe
+__device__ __forceinline__ double logaddexp64(double a, double b) {
+  double m = fmax(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1p(exp(-fabs(a - b)));
+}
+// sequence is inside the parity domain (include/nbctc.h)
+__device__ __forceinline__ bool seq_feasible(int64_t Tb, int64_t Lb, int64_t T, int64_t Lmax) {
+  return Lb >= 1 && Lb <= Lmax && Tb >= Lb && Tb <= T;
+}
+#endif
+
+}  // namespace nbctc

@@ -1,0 +1,290 @@
+// Generic (unfused) path: three kernels with HBM intermediates.  Any T, C and Lmax <= 8192.
+// This is the cross-check / fallback for shapes the fused kernel does not take; it is NOT
+// the roofline path (it moves >= 12*T*B*C bytes plus the lattice tiles).
+//
+//   K1 rowstats : one warp per (t,b) row -> row log-partition + per-state raw emission
+//                 (NoBlankCTC.py:136 log_softmax, :96-102 gather; binary: NoBlankBinaryCTC.py:109-112)
+//   K2 lattice  : one CTA per sequence, thread = state, float64 log domain alpha then beta,
+//                 gamma overwrites the emission tile (NoBlankCTC.py:71-87 transition, :58-68 read-out)
+//   K3 grad     : one warp per (t,b) row -> w*(softmax - scatter(gamma)) / w*(sigmoid - gamma.y)/C
+#include "common.cuh"
+
+namespace nbctc {
+
+namespace {
+
+constexpr int kRowWarps = 8;  // warps per CTA in the row kernels
+
+struct GenericWs {
+  float* rowc;    // (T,B)  row constant: lse (single) / mean softplus (binary)
+  float* emis;    // (T,B,Lmax) raw emission, overwritten by gamma
+  double* alpha;  // (T,B,Lmax)
+  int* bad;       // (B) label-out-of-range flag
+};
+
+__host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lmax) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  size_t o_bad = take(sizeof(int) * B);
+  size_t o_rowc = take(sizeof(float) * T * B);
+  size_t o_emis = take(sizeof(float) * T * B * Lmax);
+  size_t o_alpha = take(sizeof(double) * T * B * Lmax);
+  if (w) {
+    char* c = static_cast<char*>(base);
+    w->bad = reinterpret_cast<int*>(c + o_bad);
+    w->rowc = reinterpret_cast<float*>(c + o_rowc);
+    w->emis = reinterpret_cast<float*>(c + o_emis);
+    w->alpha = reinterpret_cast<double*>(c + o_alpha);
+  }
+  return off;
+}
+
+// ------------------------------------------------------------------------------------
+template <bool kBinary>
+__global__ void __launch_bounds__(kRowWarps * 32)
+rowstats_kernel(Problem p, GenericWs w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= p.T * p.B) return;
+  const int64_t t = row / p.B, b = row - t * p.B;
+  const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
+  if (!seq_feasible(Tb, Lb, p.T, p.Lmax)) {
+    if (t == 0 && lane == 0) w.bad[b] = 1;
+    return;
+  }
+  const float* x = p.logits + row * p.C;
+  if (t == 0) {  // validate labels once per sequence
+    int bad = 0;
+    if (!kBinary) {
+      for (int64_t s = lane; s < Lb; s += 32) {
+        int32_t l = p.labels[b * p.Lmax + s];
+        bad |= (l < 0 || l >= p.C);
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) w.bad[b] = bad;
+  }
+  if (t >= Tb) return;
+
+  if (!kBinary) {
+    float m = -INFINITY;
+    for (int64_t c = lane; c < p.C; c += 32) m = fmaxf(m, x[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int64_t c = lane; c < p.C; c += 32) s += expf(x[c] - m);
+    s = warp_sum(s);
+    if (lane == 0) w.rowc[row] = m + logf(s);
+    for (int64_t st = lane; st < Lb; st += 32) {
+      int32_t l = p.labels[b * p.Lmax + st];
+      float e = (l >= 0 && l < p.C) ? x[l] : 0.f;
+      w.emis[row * p.Lmax + st] = e;
+    }
+  } else {
+    // row constant (1/C) sum_c softplus(x_c); emission (1/C) y_s . x
+    float sp = 0.f;
+    for (int64_t c = lane; c < p.C; c += 32) {
+      float v = x[c];
+      sp += fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+    }
+    sp = warp_sum(sp);
+    const float invC = 1.f / (float)p.C;
+    if (lane == 0) w.rowc[row] = sp * invC;
+    for (int64_t st = 0; st < Lb; ++st) {
+      const float* y = p.targets + (b * p.Lmax + st) * p.C;
+      float d = 0.f;
+      for (int64_t c = lane; c < p.C; c += 32) d = fmaf(y[c], x[c], d);
+      d = warp_sum(d);
+      if (lane == 0) w.emis[row * p.Lmax + st] = d * invC;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+lattice_kernel(Problem p, GenericWs w) {
+  extern __shared__ double sm[];  // [2][Lmax]
+  const int64_t b = blockIdx.x;
+  const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
+  const int64_t B = p.B, L = p.Lmax;
+  if (!seq_feasible(Tb, Lb, p.T, L) || w.bad[b]) {
+    if (threadIdx.x == 0) p.loss[b] = INFINITY;
+    return;
+  }
+  double* a0 = sm;
+  double* a1 = sm + L;
+  const int nt = blockDim.x;
+  // ---- alpha ----
+  for (int64_t s = threadIdx.x; s < Lb; s += nt) {
+    double v = (s == 0) ? (double)w.emis[(0 * B + b) * L] - (double)w.rowc[b] : -INFINITY;
+    a0[s] = v;
+    w.alpha[(0 * B + b) * L + s] = v;
+  }
+  __syncthreads();
+  for (int64_t t = 1; t < Tb; ++t) {
+    double* prev = (t & 1) ? a0 : a1;
+    double* cur = (t & 1) ? a1 : a0;
+    const int64_t row = t * B + b;
+    const double rc = (double)w.rowc[row];
+    for (int64_t s = threadIdx.x; s < Lb; s += nt) {
+      double stay = prev[s];
+      double adv = (s > 0) ? prev[s - 1] : -INFINITY;
+      double v = logaddexp64(stay, adv) + ((double)w.emis[row * L + s] - rc);
+      cur[s] = v;
+      w.alpha[row * L + s] = v;
+    }
+    __syncthreads();
+  }
+  double* fin = ((Tb - 1) & 1) ? a1 : a0;
+  const double ll = fin[Lb - 1];
+  __syncthreads();
+  if (threadIdx.x == 0) p.loss[b] = (float)(-ll);
+  if (p.grad == nullptr) return;
+  if (!(ll > -INFINITY)) return;  // cannot happen inside the parity domain
+  // ---- beta / gamma (be = beta + emission, ping-pong in the same smem) ----
+  {
+    const int64_t row = (Tb - 1) * B + b;
+    const double rc = (double)w.rowc[row];
+    for (int64_t s = threadIdx.x; s < Lb; s += nt) {
+      double beta = (s == Lb - 1) ? 0.0 : -INFINITY;
+      double e = (double)w.emis[row * L + s] - rc;
+      double g = exp(w.alpha[row * L + s] + beta - ll);
+      w.emis[row * L + s] = (float)g;
+      a0[s] = beta + e;
+    }
+    __syncthreads();
+  }
+  int flip = 0;
+  for (int64_t t = Tb - 2; t >= 0; --t) {
+    double* prev = flip ? a1 : a0;
+    double* cur = flip ? a0 : a1;
+    const int64_t row = t * B + b;
+    const double rc = (double)w.rowc[row];
+    for (int64_t s = threadIdx.x; s < Lb; s += nt) {
+      double up = (s + 1 < Lb) ? prev[s + 1] : -INFINITY;
+      double beta = logaddexp64(prev[s], up);
+      double e = (double)w.emis[row * L + s] - rc;
+      double g = exp(w.alpha[row * L + s] + beta - ll);
+      w.emis[row * L + s] = (float)g;
+      cur[s] = beta + e;
+    }
+    __syncthreads();
+    flip ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+template <bool kBinary>
+__global__ void __launch_bounds__(kRowWarps * 32)
+grad_kernel(Problem p, GenericWs w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= p.T * p.B) return;
+  const int64_t t = row / p.B, b = row - t * p.B;
+  const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
+  float* g = p.grad + row * p.C;
+  const float lossb = p.loss[b];
+  if (!seq_feasible(Tb, Lb, p.T, p.Lmax) || t >= Tb || !(lossb < INFINITY)) {
+    for (int64_t c = lane; c < p.C; c += 32) g[c] = 0.f;
+    return;
+  }
+  const float* x = p.logits + row * p.C;
+  float wgt = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f);
+  const float* gam = w.emis + row * p.Lmax;
+  if (!kBinary) {
+    const float lse = w.rowc[row];
+    for (int64_t c = lane; c < p.C; c += 32) g[c] = wgt * expf(x[c] - lse);
+    __syncwarp();
+    for (int64_t s = lane; s < Lb; s += 32) {
+      int32_t l = p.labels[b * p.Lmax + s];
+      atomicAdd(&g[l], -wgt * gam[s]);
+    }
+  } else {
+    wgt /= (float)p.C;
+    for (int64_t c = lane; c < p.C; c += 32) {
+      float acc = 1.f / (1.f + expf(-x[c]));
+      const float* y = p.targets + b * p.Lmax * p.C + c;
+      for (int64_t s = 0; s < Lb; ++s) acc = fmaf(-gam[s], y[s * p.C], acc);
+      g[c] = wgt * acc;
+    }
+  }
+}
+
+__global__ void reduce_loss_kernel(const float* __restrict__ loss, const float* __restrict__ seq_w, float w_scalar,
+                                   int64_t B, double* __restrict__ sum_out, float* __restrict__ reduced_out) {
+  // one CTA, fixed-order tree => bit-reproducible
+  __shared__ double sh[2][32];
+  double acc = 0.0, wacc = 0.0;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+    double l = (double)loss[i];
+    acc += l;
+    wacc += seq_w ? l * (double)seq_w[i] : l;
+  }
+  acc = warp_sum(acc);
+  wacc = warp_sum(wacc);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = acc; sh[1][threadIdx.x >> 5] = wacc; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool in = threadIdx.x < (blockDim.x >> 5);
+    double v = warp_sum(in ? sh[0][threadIdx.x] : 0.0);
+    double wv = warp_sum(in ? sh[1][threadIdx.x] : 0.0);
+    if (threadIdx.x == 0) {
+      if (sum_out) *sum_out = v;
+      if (reduced_out) *reduced_out = (float)(wv * (double)w_scalar);
+    }
+  }
+}
+
+}  // namespace
+
+size_t generic_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  (void)C;
+  return carve(nullptr, nullptr, T, B, Lmax);
+}
+
+int reduce_loss_launch(const Problem& p, cudaStream_t stream) {
+  reduce_loss_kernel<<<1, 1024, 0, stream>>>(p.loss, p.seq_w, p.w_scalar, p.B, p.loss_sum, p.loss_reduced);
+  NBCTC_LAUNCH_CHECK();
+  return NBCTC_OK;
+}
+
+int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (p.Lmax > 8192) {
+    set_error("generic path supports Lmax <= 8192 (got %lld)", (long long)p.Lmax);
+    return NBCTC_ERR_UNSUPPORTED;
+  }
+  GenericWs w;
+  size_t need = carve(&w, ws, p.T, p.B, p.Lmax);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    return NBCTC_ERR_WORKSPACE;
+  }
+  const int64_t rows = p.T * p.B;
+  const unsigned row_blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+  if (binary)
+    rowstats_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
+  else
+    rowstats_kernel<false><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
+  NBCTC_LAUNCH_CHECK();
+
+  int nt = (int)std::min<int64_t>(1024, (p.Lmax + 31) / 32 * 32);
+  size_t smem = 2 * sizeof(double) * p.Lmax;
+  if (smem > 48 * 1024)
+    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lattice_kernel<<<(unsigned)p.B, nt, smem, stream>>>(p, w);
+  NBCTC_LAUNCH_CHECK();
+
+  if (p.grad) {
+    if (binary)
+      grad_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
+    else
+      grad_kernel<false><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
+    NBCTC_LAUNCH_CHECK();
+  }
+  return NBCTC_OK;
+}
+
+}  // namespace nbctc

@@ -1,0 +1,158 @@
+"""torch.autograd.Function wrappers around the C ABI (PyTorch = tensor plumbing only).
+
+Follows the reference's own Function idiom (models/layers/BalanceLabels.py:11-21:
+staticmethod forward/backward, tuple of grads).  The gradient with respect to the logits is
+produced by the same fused kernel that computes the loss (one read of the logits, one write
+of the gradient); ``backward`` only rescales it by the upstream gradient, and that rescale is
+skipped on the device when the upstream gradient is exactly 1 (``loss.backward()``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _ffi
+
+_REDUCTIONS = ("mean", "sum", "none")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _prep_lengths(t, device, B, name):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if t.numel() != B:
+        raise ValueError(f"{name} must have {B} elements, got {tuple(t.shape)}")
+    return t.reshape(B).to(device=device, dtype=torch.int64).contiguous()
+
+
+def _launch(x, targets, in_len, tgt_len, binary, want_grad, w_scalar, seq_w, flags):
+    """Run the fused loss(+grad) on the current stream.  Returns (per_seq, sum64, reduced, grad)."""
+    T, B, C = x.shape
+    Lmax = targets.shape[1]
+    dev = x.device
+    lib = _ffi.lib()
+    per_seq = torch.empty(B, dtype=torch.float32, device=dev)
+    loss_sum = torch.empty((), dtype=torch.float64, device=dev)
+    reduced = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(x) if want_grad else None
+    if not want_grad:
+        flags |= _ffi.FLAG_NO_GRAD
+    ws_bytes = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 1 if binary else 0, flags))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    fn = lib.nbbctc_loss_grad_f32 if binary else lib.nbctc_loss_grad_f32
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = fn(x.data_ptr(), T, B, C, targets.data_ptr(), Lmax, in_len.data_ptr(), tgt_len.data_ptr(),
+                per_seq.data_ptr(), loss_sum.data_ptr(), reduced.data_ptr(), _ptr(grad), _ptr(seq_w),
+                float(w_scalar), ws.data_ptr(), ws_bytes, flags, stream)
+    _ffi.check(rc, "nbbctc_loss_grad_f32" if binary else "nbctc_loss_grad_f32")
+    return per_seq, loss_sum, reduced, grad
+
+
+class _NoBlankCTCFunction(torch.autograd.Function):
+    """forward(logits, targets, input_length, target_length, reduction, binary, total_batch, flags, out64, want_grad)"""
+
+    @staticmethod
+    def forward(ctx, logits, targets, input_length, target_length, reduction, binary, total_batch, flags, out64,
+                want_grad):
+        if reduction not in _REDUCTIONS:
+            raise ValueError(f"reduction must be one of {_REDUCTIONS}, got {reduction!r}")
+        if logits.dim() != 3:
+            raise ValueError(f"logits must be (T,B,C), got {tuple(logits.shape)}")
+        if not logits.is_cuda:
+            raise _ffi.NbctcError("ctc_b200 is CUDA-only: logits must be a CUDA tensor (there is no CPU fallback)")
+        T, B, C = logits.shape
+        dev = logits.device
+        x = logits.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if binary:
+            if targets.dim() != 3 or targets.shape[0] != B or targets.shape[2] != C:
+                raise ValueError(f"multi-hot targets must be (B,Lmax,C)=({B},L,{C}), got {tuple(targets.shape)}")
+            tg = targets.detach().to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            if targets.dim() != 2 or targets.shape[0] != B:
+                raise ValueError(f"labels must be (B,Lmax)=({B},L), got {tuple(targets.shape)}")
+            tg = targets.detach().to(device=dev, dtype=torch.int32).contiguous()
+        il = _prep_lengths(input_length, dev, B, "input_length")
+        tl = _prep_lengths(target_length, dev, B, "target_length")
+        # grad mode is always off inside forward(); the caller samples it (validate() runs under no_grad)
+        want_grad = bool(want_grad) and bool(ctx.needs_input_grad[0])
+        nb = int(total_batch) if total_batch else B
+        w = 1.0 / nb if reduction == "mean" else 1.0
+        per_seq, loss_sum, reduced, grad = _launch(x, tg, il, tl, binary, want_grad, w, None, int(flags))
+        ctx.grad = grad
+        ctx.per_seq_out = reduction == "none"
+        ctx.in_dtype = logits.dtype
+        ctx.shape = (T, B, C)
+        if reduction == "none":
+            return per_seq
+        if out64:
+            return loss_sum * w
+        return reduced
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        grad = ctx.grad
+        if grad is None:
+            raise RuntimeError("NoBlankCTC backward called twice (or without a gradient buffer); "
+                               "the fused gradient is consumed by the first backward")
+        ctx.grad = None
+        T, B, C = ctx.shape
+        go = grad_out.detach().to(device=grad.device, dtype=torch.float32).contiguous()
+        lib = _ffi.lib()
+        with torch.cuda.device(grad.device):
+            stream = torch.cuda.current_stream(grad.device).cuda_stream
+            rc = lib.nbctc_scale_grad_f32(grad.data_ptr(), T, B, C, go.data_ptr(), 1 if ctx.per_seq_out else 0, stream)
+        _ffi.check(rc, "nbctc_scale_grad_f32")
+        if grad.dtype != ctx.in_dtype:
+            grad = grad.to(ctx.in_dtype)
+        return grad, None, None, None, None, None, None, None, None, None
+
+
+def no_blank_ctc_loss(logits, labels, input_length, target_length, reduction="mean", *, total_batch=None,
+                      flags=_ffi.FLAG_DEFAULT, out64=False):
+    """Functional form of :class:`ctc_b200.NoBlankCTC` (NoBlankCTC.py:129-141)."""
+    want_grad = torch.is_grad_enabled() and logits.requires_grad
+    return _NoBlankCTCFunction.apply(logits, labels, input_length, target_length, reduction, False, total_batch,
+                                     flags, out64, want_grad)
+
+
+def no_blank_binary_ctc_loss(logits, targets, input_length, target_length, reduction="mean", *, total_batch=None,
+                             flags=_ffi.FLAG_DEFAULT, out64=False):
+    """Functional form of :class:`ctc_b200.NoBlankBinaryCTC` (NoBlankBinaryCTC.py:139-151)."""
+    want_grad = torch.is_grad_enabled() and logits.requires_grad
+    return _NoBlankCTCFunction.apply(logits, targets, input_length, target_length, reduction, True, total_batch,
+                                     flags, out64, want_grad)
+
+
+def best_path(logits, labels, input_length, target_length, want_argmax=True):
+    """Viterbi alignment on the no-blank lattice + per-frame argmax.
+
+    Returns ``(states (B,T) int32, score (B,) float64, argmax (T,B) int32 or None)``.
+    """
+    if not logits.is_cuda:
+        raise _ffi.NbctcError("ctc_b200 is CUDA-only")
+    T, B, C = logits.shape
+    dev = logits.device
+    x = logits.detach().float().contiguous()
+    lab = labels.detach().to(device=dev, dtype=torch.int32).contiguous()
+    Lmax = lab.shape[1]
+    il = _prep_lengths(input_length, dev, B, "input_length")
+    tl = _prep_lengths(target_length, dev, B, "target_length")
+    states = torch.empty((B, T), dtype=torch.int32, device=dev)
+    score = torch.empty(B, dtype=torch.float64, device=dev)
+    amax = torch.empty((T, B), dtype=torch.int32, device=dev) if want_argmax else None
+    lib = _ffi.lib()
+    ws_bytes = int(lib.nbctc_best_path_workspace_bytes(T, B, C, Lmax))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.nbctc_best_path_i32(x.data_ptr(), T, B, C, lab.data_ptr(), Lmax, il.data_ptr(), tl.data_ptr(),
+                                     states.data_ptr(), score.data_ptr(), _ptr(amax), ws.data_ptr(), ws_bytes, stream)
+    _ffi.check(rc, "nbctc_best_path_i32")
+    return states, score, amax

@@ -1,0 +1,153 @@
+/*
+ * nbctc.h -- C ABI of the B200-native no-blank CTC loss library (libnbctc.so).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates: the
+ * forward/backward dynamic programme of gotaku6629/CTC's no-blank CTC losses.  The
+ * reference has no native code and no FFI of its own (it is pure PyTorch); each entry
+ * point below names the reference Python interface it replaces (file:line under the
+ * reference tree) -- that is what a maintainer binds it to.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in
+ *     `_host`; the library never allocates, frees or retains caller memory (the `_host`
+ *     convenience entry points are the one exception: they own temporary device buffers
+ *     for the duration of the call);
+ *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it and no
+ *     entry point synchronises the host (except the `_host` ones);
+ *   - return value: 0 on success, negative NBCTC_ERR_* otherwise; a human-readable
+ *     message for the calling thread is available from nbctc_last_error();
+ *   - layouts: logits/grad (T,B,C) row-major contiguous float32; labels (B,Lmax) int32,
+ *     slots >= target_length[b] are never dereferenced (the reference pads them with -1);
+ *     multi-hot targets (B,Lmax,C) float32; lengths (B) int64.
+ *   - parity domain: 1 <= target_length[b] <= input_length[b] <= T and labels in [0,C).
+ *     Sequences outside it get loss = +inf and an all-zero gradient (the reference
+ *     returns ~1e13 and meaningless gradients there).
+ */
+#ifndef NBCTC_H_
+#define NBCTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBCTC_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define NBCTC_OK 0
+#define NBCTC_ERR_INVALID_ARG (-1)
+#define NBCTC_ERR_UNSUPPORTED (-2)
+#define NBCTC_ERR_WORKSPACE (-3)
+#define NBCTC_ERR_CUDA (-4)
+
+/* flags */
+#define NBCTC_FLAG_DEFAULT 0u
+#define NBCTC_FLAG_GENERIC 1u     /* force the unfused three-kernel path (debug / cross-check) */
+#define NBCTC_FLAG_NO_GRAD 2u     /* loss only (validate(), train.py:486,576 runs under no_grad) */
+
+typedef void* nbctc_stream_t; /* cudaStream_t */
+
+/* Library version (NBCTC_VERSION of the build). */
+int nbctc_version(void);
+
+/* Last error message of the calling thread ("" if none). Never NULL. */
+const char* nbctc_last_error(void);
+
+/* Bytes of scratch the caller must provide for one call with these shapes.
+ * `binary` = 0 for nbctc_*, 1 for nbbctc_*.  Returns 0 on invalid shapes. */
+size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int binary, uint32_t flags);
+
+/*
+ * NoBlankCTC forward (+ gradient).  Replaces NoBlankCTC.forward (NoBlankCTC.py:129-141:
+ * log_softmax :136, calc_trans :90-126, computes_transition :71-87, read-out :58-68,:139)
+ * and the autograd graph behind it (train.py:444 Loss.backward()).
+ *
+ *   loss_per_seq[b] = -log p(l_b | x_b)                                  (b < B)
+ *   grad_logits[t,b,c] = w_b * (softmax(x[t,b,:])[c] - sum_{s: l_s = c} gamma_t(s))   for t < input_length[b]
+ *                      = 0                                                            otherwise
+ *   w_b = weight_scalar * (seq_weights ? seq_weights[b] : 1)
+ * The reference's mean over the batch (NoBlankCTC.py:140) is weight_scalar = 1/B.
+ * grad_logits may be NULL (or NBCTC_FLAG_NO_GRAD set) to skip the backward half.
+ * loss_sum (nullable) receives sum_b loss_per_seq[b] accumulated in float64 in a fixed
+ * order (bit-reproducible; this is the scalar that is all-reduced across GPUs).
+ * loss_reduced (nullable) receives (float)(weight_scalar * loss_sum), i.e. the reference's
+ * return value torch.mean(loss) (NoBlankCTC.py:140) when weight_scalar = 1/B.
+ */
+int nbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C,
+                        const int32_t* labels, int64_t Lmax,
+                        const int64_t* input_lengths, const int64_t* target_lengths,
+                        float* loss_per_seq, double* loss_sum, float* loss_reduced,
+                        float* grad_logits, const float* seq_weights, float weight_scalar,
+                        void* workspace, size_t workspace_bytes, uint32_t flags,
+                        nbctc_stream_t stream);
+
+/*
+ * NoBlankBinaryCTC forward (+ gradient).  Replaces NoBlankBinaryCTC.forward
+ * (NoBlankBinaryCTC.py:139-151: sigmoid :146, BCELoss emissions :109-112/:85-88,
+ * transition :72-95, read-out :58-68,:149).
+ *   e[t,b,s] = (1/C) sum_c [ y log sigmoid(x) + (1-y) log(1-sigmoid(x)) ]
+ *   grad_logits[t,b,c] = w_b * (sigmoid(x[t,b,c]) - sum_s gamma_t(s) y[b,s,c]) / C   for t < input_length[b]
+ * targets: (B,Lmax,C) float32 in [0,1]; rows >= target_length[b] are ignored.
+ */
+int nbbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C,
+                         const float* targets, int64_t Lmax,
+                         const int64_t* input_lengths, const int64_t* target_lengths,
+                         float* loss_per_seq, double* loss_sum, float* loss_reduced,
+                         float* grad_logits, const float* seq_weights, float weight_scalar,
+                         void* workspace, size_t workspace_bytes, uint32_t flags,
+                         nbctc_stream_t stream);
+
+/*
+ * Backward-time rescale of a gradient produced by *_loss_grad_f32 with the upstream
+ * gradient that autograd hands to backward() (train.py:444).  grad[t,b,c] *= g where
+ * g = grad_out[0] (per_seq == 0) or grad_out[b] (per_seq != 0).  When per_seq == 0 and
+ * grad_out[0] == 1.0f the kernel exits without touching memory (decided on the device,
+ * no host sync).
+ */
+int nbctc_scale_grad_f32(float* grad_logits, int64_t T, int64_t B, int64_t C,
+                         const float* grad_out, int per_seq, nbctc_stream_t stream);
+
+/*
+ * Best (Viterbi) monotone alignment on the same lattice and per-frame argmax class
+ * (the reference has no implementation -- the intended use is
+ * imgs/ctc_action.png and the top-k on logits at train.py:41-56,434).
+ *   states[b,t] = state index of the max-score path at frame t (t < input_length[b]), -1 otherwise
+ *   score[b]    = sum_t x[t,b,label[b,states[b,t]]] in float64 (nullable)
+ *   argmax[t,b] = argmax_c x[t,b,c], ties -> lowest c (nullable)
+ * Scores use the raw logits in float64 (the row log-partition is common to all paths),
+ * ties prefer staying in the state; results are bit-exact against the float64 oracle.
+ */
+int nbctc_best_path_i32(const float* logits, int64_t T, int64_t B, int64_t C,
+                        const int32_t* labels, int64_t Lmax,
+                        const int64_t* input_lengths, const int64_t* target_lengths,
+                        int32_t* states, double* score, int32_t* argmax,
+                        void* workspace, size_t workspace_bytes, nbctc_stream_t stream);
+
+/* Workspace for nbctc_best_path_i32. */
+size_t nbctc_best_path_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+
+/*
+ * Host-buffer convenience entry points (every pointer is a HOST pointer): copy in,
+ * run on `device`, copy the loss (and the gradient when grad_logits_host != NULL) back,
+ * synchronise.  For non-PyTorch hosts and for end-to-end timing.
+ */
+int nbctc_loss_grad_host_f32(int device, const float* logits_host, int64_t T, int64_t B, int64_t C,
+                             const int32_t* labels_host, int64_t Lmax,
+                             const int64_t* input_lengths_host, const int64_t* target_lengths_host,
+                             float* loss_per_seq_host, double* loss_sum_host, float* loss_reduced_host,
+                             float* grad_logits_host, float weight_scalar, uint32_t flags);
+
+int nbbctc_loss_grad_host_f32(int device, const float* logits_host, int64_t T, int64_t B, int64_t C,
+                              const float* targets_host, int64_t Lmax,
+                              const int64_t* input_lengths_host, const int64_t* target_lengths_host,
+                              float* loss_per_seq_host, double* loss_sum_host, float* loss_reduced_host,
+                              float* grad_logits_host, float weight_scalar, uint32_t flags);
+
+/* Number of kernels this library has launched in the calling process (diagnostics / bench). */
+uint64_t nbctc_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBCTC_H_ */

@@ -1,0 +1,276 @@
+"""GPU parity: the CUDA path (through the nn.Module -> ctypes -> C ABI) against the float64 oracle
+and the reference-generated golden fixtures.  Tolerance (BASELINE.json north_star): loss and
+gradient within 1e-5 relative of the float64 reference; integer outputs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from helpers import make_bctc_case, make_ctc_case
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import ctc_b200
+    assert torch.cuda.is_available()
+    return ctc_b200
+
+
+def run_cuda(nb, kind, x, tg, il, tl, reduction="mean", flags=0, lab_dtype=torch.int32):
+    xt = torch.tensor(x, device=DEV, requires_grad=True)
+    if kind == "ctc":
+        m = nb.NoBlankCTC(reduction=reduction, flags=flags)
+        tgt = torch.tensor(np.asarray(tg), device=DEV).to(lab_dtype)
+    else:
+        m = nb.NoBlankBinaryCTC(reduction=reduction, flags=flags)
+        tgt = torch.tensor(np.asarray(tg), device=DEV).float()
+    loss = m(xt, tgt, torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV))
+    (loss.sum() if reduction == "none" else loss).backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu().double().numpy(), xt.grad.detach().cpu().double().numpy()
+
+
+def oracle(kind, x, tg, il, tl, reduction="mean"):
+    f = R.nbctc_loss_grad if kind == "ctc" else R.nbbctc_loss_grad
+    return f(x, tg, il, tl, reduction)
+
+
+def assert_parity(loss, grad, ref, tol=TOL):
+    rl = np.max(np.abs(loss - ref["loss"]) / np.abs(ref["loss"]))
+    rg = rel_l2(grad, ref["grad"])
+    assert rl < tol, f"loss rel err {rl}"
+    assert rg < tol, f"grad L2 rel err {rg}"
+    # Linf relative to the largest gradient entry, reported bound 5e-5
+    linf = np.max(np.abs(grad - ref["grad"])) / np.max(np.abs(ref["grad"]))
+    assert linf < 5 * tol, f"grad Linf rel err {linf}"
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+def test_golden_fixtures(nb, golden, flags):
+    kind = str(golden["kind"])
+    loss, grad = run_cuda(nb, kind, golden["logits"], golden["targets"], golden["input_length"],
+                          golden["target_length"], flags=flags)
+    assert abs(loss - float(golden["loss"])) / abs(float(golden["loss"])) < TOL
+    assert rel_l2(grad, golden["grad"]) < TOL
+
+
+CTC_SHAPES = [
+    # T, B, C, Lmax, ragged_T, dup
+    (1, 3, 5, 1, False, False),
+    (7, 1, 3, 7, False, False),
+    (64, 8, 157, 8, False, False),        # cfg1
+    (64, 8, 157, 8, True, True),
+    (33, 5, 33, 31, True, False),         # --v-class 33
+    (50, 6, 10, 32, True, True),
+    (40, 4, 157, 40, True, False),        # Lmax > 32
+    (96, 3, 64, 64, True, False),
+    (130, 2, 1024, 100, True, False),
+    (300, 2, 40, 256, True, False),       # cfg4-style state count
+    (257, 9, 157, 17, True, False),
+    (512, 4, 157, 64, True, False),       # cfg5-style
+    (20, 7, 1, 1, False, False),          # single class
+    (24, 5, 4, 300, True, False),         # Lmax > 256 (clamped to T)
+]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+@pytest.mark.parametrize("shape", CTC_SHAPES, ids=lambda s: "T%d_B%d_C%d_L%d_%d%d" % s)
+def test_ctc_random_vs_oracle(nb, shape, flags):
+    T, B, C, L, ragged, dup = shape
+    x, lab, il, tl = make_ctc_case(100 + T + L, T, B, C, L, ragged_T=ragged, dup=dup)
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl, flags=flags)
+    assert_parity(loss, grad, oracle("ctc", x, lab, il, tl))
+
+
+BCTC_SHAPES = [
+    (1, 2, 5, 1, 0.3),
+    (64, 8, 157, 8, 0.03),
+    (33, 5, 33, 31, 0.1),
+    (40, 4, 157, 40, 0.03),
+    (60, 3, 157, 32, 0.5),
+    (100, 2, 300, 70, 0.02),
+    (257, 5, 157, 17, 0.03),
+]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+@pytest.mark.parametrize("shape", BCTC_SHAPES, ids=lambda s: "T%d_B%d_C%d_L%d_p%g" % s)
+def test_bctc_random_vs_oracle(nb, shape, flags):
+    T, B, C, L, dens = shape
+    x, y, il, tl = make_bctc_case(200 + T + L, T, B, C, L, density=dens)
+    loss, grad = run_cuda(nb, "bctc", x, y, il, tl, flags=flags)
+    assert_parity(loss, grad, oracle("bctc", x, y, il, tl))
+
+
+def test_bctc_soft_targets_and_minus_one_padding(nb):
+    """Targets need not be {0,1}; padded rows hold -1 in the reference's dataset
+    (charades_ctc_pred.py:557-559) and must be ignored, not dereferenced into the maths."""
+    T, B, C, L = 30, 4, 21, 6
+    x, y, il, tl = make_bctc_case(7, T, B, C, L, density=0.2, pad=-1.0)
+    rs = np.random.RandomState(1)
+    soft = rs.uniform(size=y.shape).astype(np.float32)
+    y_soft = np.where(y < 0, y, soft)
+    for tg in (y, y_soft):
+        loss, grad = run_cuda(nb, "bctc", x, tg, il, tl)
+        clean = np.where(tg < 0, 0.0, tg)
+        assert_parity(loss, grad, oracle("bctc", x, clean, il, tl))
+
+
+@pytest.mark.parametrize("kind", ["ctc", "bctc"])
+@pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
+def test_reductions(nb, kind, reduction):
+    if kind == "ctc":
+        x, tg, il, tl = make_ctc_case(5, 40, 6, 20, 9)
+    else:
+        x, tg, il, tl = make_bctc_case(5, 40, 6, 20, 9, density=0.1)
+    loss, grad = run_cuda(nb, kind, x, tg, il, tl, reduction=reduction)
+    ref = oracle(kind, x, tg, il, tl, reduction)
+    assert_parity(loss, grad, ref)
+
+
+def test_edge_lengths(nb):
+    """L_b = 1, L_b = T_b (single admissible path), T_b < T (zero rows), -1 padding, int64 labels."""
+    T, B, C, L = 12, 5, 9, 12
+    rs = np.random.RandomState(3)
+    x = rs.standard_normal((T, B, C)).astype(np.float32)
+    tl = np.array([1, 12, 5, 5, 3])
+    il = np.array([12, 12, 5, 9, 3])
+    lab = rs.randint(0, C, size=(B, L)).astype(np.int64)
+    for b in range(B):
+        lab[b, tl[b]:] = -1
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl, lab_dtype=torch.int64)
+    ref = oracle("ctc", x, lab, il, tl)
+    assert_parity(loss, grad, ref)
+    for b in range(B):
+        assert np.all(grad[il[b]:, b] == 0.0)           # exact zeros beyond input_length (quirk 4)
+    # single admissible path: gamma is one-hot => grad = (softmax - onehot)/B
+    b = 1
+    sm = np.exp(R.log_softmax(x[:, b].astype(np.float64)))
+    oh = np.zeros_like(sm)
+    oh[np.arange(T), lab[b, :T]] = 1.0
+    np.testing.assert_allclose(grad[:, b], (sm - oh) / B, atol=2e-7)
+
+
+def test_infeasible_sequences(nb):
+    """Outside the parity domain (T_b < L_b, L_b = 0, label out of range): loss = +inf, grad = 0,
+    and the other sequences of the batch are unaffected."""
+    T, B, C, L = 8, 5, 6, 10
+    x, lab, il, tl = make_ctc_case(9, T, B, C, L, ragged_T=False)
+    tl[:] = [3, 10, 0, 2, 2]
+    il[:] = [8, 8, 8, 8, 8]
+    lab[:] = np.random.RandomState(1).randint(0, C, size=(B, L))
+    lab[3, 1] = C + 3
+    m = nb.NoBlankCTC(reduction="none")
+    xt = torch.tensor(x, device=DEV, requires_grad=True)
+    per = m(xt, torch.tensor(lab, device=DEV), torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV))
+    per[[0, 4]].sum().backward()
+    torch.cuda.synchronize()
+    per = per.detach().cpu().numpy()
+    assert np.isinf(per[1]) and np.isinf(per[2]) and np.isinf(per[3])
+    g = xt.grad.cpu().numpy()
+    assert np.all(g[:, 1:4] == 0.0)
+    ok = [0, 4]
+    ref = R.nbctc_loss_grad(x[:, ok], lab[ok], il[ok], tl[ok], "none")
+    np.testing.assert_allclose(per[ok], ref["per_seq"], rtol=TOL)
+    assert rel_l2(g[:, ok], ref["grad"]) < TOL
+
+
+def test_upstream_gradient_scaling_and_no_grad(nb):
+    x, lab, il, tl = make_ctc_case(17, 30, 4, 11, 6)
+    ref = oracle("ctc", x, lab, il, tl)
+    m = nb.NoBlankCTC()
+    args = (torch.tensor(lab, device=DEV), torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV))
+    xt = torch.tensor(x, device=DEV, requires_grad=True)
+    (2.5 * m(xt, *args)).backward()
+    assert rel_l2(xt.grad.cpu().numpy(), 2.5 * ref["grad"]) < TOL
+    with torch.no_grad():
+        l2 = m(xt, *args)
+    assert not l2.requires_grad and abs(float(l2) - ref["loss"]) / ref["loss"] < TOL
+    # validate(): logits without grad
+    l3 = m(xt.detach(), *args)
+    assert not l3.requires_grad
+    # float64 logits are accepted; the gradient comes back in the input dtype
+    xd = torch.tensor(x, device=DEV, dtype=torch.float64, requires_grad=True)
+    m(xd, *args).backward()
+    assert xd.grad.dtype == torch.float64 and rel_l2(xd.grad.cpu().numpy(), ref["grad"]) < TOL
+    # non-contiguous logits (B,T,C)->(T,B,C) view
+    xb = torch.tensor(np.ascontiguousarray(x.transpose(1, 0, 2)), device=DEV, requires_grad=True)
+    m(xb.transpose(0, 1), *args).backward()
+    assert rel_l2(xb.grad.cpu().numpy().transpose(1, 0, 2), ref["grad"]) < TOL
+    assert len(m.state_dict()) == 0
+
+
+def test_fused_matches_generic_bitwise_properties(nb):
+    """Size-independent properties at a larger size: rows of the gradient sum to zero
+    (softmax and gamma both sum to one), zero rows beyond input_length, default == generic."""
+    T, B, C, L = 256, 512, 157, 32
+    x, lab, il, tl = make_ctc_case(1234, T, B, C, L, ragged_T=True)
+    l0, g0 = run_cuda(nb, "ctc", x, lab, il, tl, flags=0)
+    l1, g1 = run_cuda(nb, "ctc", x, lab, il, tl, flags=1)
+    assert abs(l0 - l1) / abs(l1) < 1e-6
+    assert rel_l2(g0, g1) < 2e-6
+    rowsum = np.abs(g0.sum(axis=2)) * B
+    assert rowsum.max() < 1e-5
+    live = np.arange(T)[:, None] < il[None, :]
+    assert np.all(g0[~live] == 0.0)
+    sub = np.random.RandomState(0).choice(B, 24, replace=False)
+    ref = R.nbctc_loss_grad(x[:, sub], lab[sub], il[sub], tl[sub], "sum")
+    assert rel_l2(g0[:, sub] * B, ref["grad"]) < TOL
+
+
+def test_best_path_and_argmax_bit_exact(nb):
+    for seed, (T, B, C, L) in enumerate([(4, 2, 5, 3), (64, 8, 157, 8), (200, 6, 33, 40), (90, 3, 1024, 64)]):
+        x, lab, il, tl = make_ctc_case(40 + seed, T, B, C, L, ragged_T=True, dup=(seed % 2 == 1))
+        st, sc, am = nb.best_path(torch.tensor(x, device=DEV), torch.tensor(lab, device=DEV),
+                                  torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV))
+        torch.cuda.synchronize()
+        rst, rsc = R.best_path(x, lab, il, tl)
+        assert np.array_equal(st.cpu().numpy(), rst)
+        assert np.array_equal(sc.cpu().numpy(), rsc)          # float64 add/max only: bit-exact
+        assert np.array_equal(am.cpu().numpy(), R.frame_argmax(x))
+
+
+def test_kat_c_alignment(nb):
+    from conftest import load_golden
+    a = load_golden("kat_a_ctc")
+    st, sc, am = nb.best_path(torch.tensor(a["logits"], device=DEV), torch.tensor(a["targets"], device=DEV),
+                              torch.tensor(a["input_length"], device=DEV), torch.tensor(a["target_length"], device=DEV))
+    assert st.cpu().tolist() == [[0, 0, 1, 2], [0, 0, 0, 1]]
+    assert am.cpu().numpy().T.tolist() == [[1, 4, 2, 3], [4, 1, 3, 2]]
+
+
+def test_c_abi_host_entry_points(nb):
+    """Call the C ABI directly with HOST buffers (numpy) -- no torch types cross the boundary."""
+    import ctypes as C
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    x, lab, il, tl = make_ctc_case(3, 20, 4, 13, 5)
+    T, B, Cc = x.shape
+    per = np.zeros(B, np.float32)
+    s64 = np.zeros(1, np.float64)
+    red = np.zeros(1, np.float32)
+    g = np.zeros_like(x)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.nbctc_loss_grad_host_f32(0, p(x), T, B, Cc, p(lab), lab.shape[1], p(il), p(tl), p(per), p(s64), p(red),
+                                      p(g), 1.0 / B, 0)
+    assert rc == 0, lib.nbctc_last_error()
+    ref = R.nbctc_loss_grad(x, lab, il, tl)
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    assert abs(red[0] - ref["loss"]) / ref["loss"] < TOL and abs(s64[0] / B - ref["loss"]) / ref["loss"] < TOL
+    assert rel_l2(g, ref["grad"]) < TOL
+    xb, y, ilb, tlb = make_bctc_case(4, 20, 4, 13, 5, density=0.2)
+    rc = lib.nbbctc_loss_grad_host_f32(0, p(xb), T, B, Cc, p(y), y.shape[1], p(ilb), p(tlb), p(per), p(s64), p(red),
+                                       p(g), 1.0 / B, 0)
+    assert rc == 0, lib.nbctc_last_error()
+    refb = R.nbbctc_loss_grad(xb, y, ilb, tlb)
+    assert abs(red[0] - refb["loss"]) / refb["loss"] < TOL and rel_l2(g, refb["grad"]) < TOL
+    # error path: bad shape -> negative code + message, nothing thrown
+    rc = lib.nbctc_loss_grad_host_f32(0, p(x), 0, B, Cc, p(lab), lab.shape[1], p(il), p(tl), p(per), p(s64), p(red),
+                                      p(g), 1.0, 0)
+    assert rc == -1 and b"invalid shape" in lib.nbctc_last_error()
