@@ -36,4 +36,4 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b.ravel())
-    return float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
+    return float(np.linalg.norm((a - b).ravel()) / (den if den > 1e-12 else 1.0))
