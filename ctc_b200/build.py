@@ -48,15 +48,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ into ctc_b200/libnbctc.so.  Returns the path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB + ".tmp", *sources()]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+            return obj, ""
+        cmd = [_nvcc(), *flags, *inc, "-c", "-o", obj, src] + (["-Xptxas", "-v"] if verbose else [])
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd), file=sys.stderr)
+        for _, err in results:
+            print(err, file=sys.stderr)
+    cmd = [_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp", *[o for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(LIB + ".tmp", LIB)
     return LIB
 

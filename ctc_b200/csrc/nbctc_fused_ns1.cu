@@ -1,0 +1,5 @@
+// Instantiations of the fused kernel for NS = 1 states per chain lane (Lmax <= 32).
+#include "fused_kernel.cuh"
+namespace nbctc {
+int launch_fused_ns1(const Problem& p, const FusedCfg& cfg, cudaStream_t stream) { return fused::launch_ns<1>(p, cfg, stream); }
+}  // namespace nbctc
