@@ -15,22 +15,27 @@
 
 namespace nbctc {
 
-constexpr int kTT = 8;      // time steps per tile
-constexpr int kMaxBuf = 8;  // tile ring depth upper bound
-constexpr int kNW = 4;      // row warps per CTA
+constexpr int kTT = 8;        // time steps per tile
+constexpr int kMaxBuf = 8;    // p-/gamma-tile ring depth upper bound
+constexpr int kMaxSlot = 16;  // row-tile (TMA) ring depth upper bound
+constexpr int kNW = 4;        // row warps per CTA
+constexpr int kThreads = 32 * (kNW + 2);  // chain warp + row warps + TMA producer warp
 
 struct FusedCfg {
   int NS, Lpad;
   int LPR, CPL, NSEG;
-  int NBUF;         // tile ring depth
+  int NBUFP, NBUFG; // p-tile / gamma-tile ring depths
+  int NSLOT;        // row-tile ring depth (TMA bulk copies land here)
+  int RS;           // bytes per row slot = 16 * max chunks per row
   int NTmax;        // ceil(T / kTT)
   int Cd;           // floats per scatter buffer
   int ckpt_global;  // checkpoints live in the workspace instead of shared memory
   int lse_global;
-  uint32_t o_bar, o_lab, o_lse, o_ckpt, o_cke, o_ptile, o_gtile, o_atile, o_delta, smem_bytes;
+  uint32_t o_bar, o_lab, o_lse, o_ckpt, o_cke, o_ptile, o_gtile, o_atile, o_delta, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
   int* ws_cke;      // [B][NTmax]
   float* ws_lse;    // [B][T]
+  const float* logits_end;  // one past the last logit (bulk copies never read past its 16-byte round-up)
 };
 
 int launch_fused_ns1(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
@@ -52,6 +57,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, 16-byte aligned, size multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
@@ -119,7 +135,8 @@ __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the
 }
 
 struct Smem {
-  uint64_t *pfull, *pempty, *gfull, *gempty;
+  uint64_t *pfull, *pempty, *gfull, *gempty, *sfull, *sempty;
+  unsigned char* ring;
   int* lab;
   float* lse;
   double* ckpt;
@@ -176,7 +193,7 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
   constexpr int Lpad = 32 * NS;
   constexpr bool kRegTile = NS <= 2;  // tile-local alpha replay in registers
   const int NT = (Tb + kTT - 1) / kTT;
-  const int NBUF = cfg.NBUF;
+  const int NBUF = cfg.NBUFP, NBUFG = cfg.NBUFG;
   double* ck = (cfg.ckpt_global ? cfg.ws_ckpt + ((size_t)b * cfg.NTmax) * Lpad : S.ckpt) + lane;
   int* cke = cfg.ckpt_global ? cfg.ws_cke + (size_t)b * cfg.NTmax : S.cke;
   double a[NS];
@@ -236,7 +253,7 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
     const int k = NT - 1 - j2;
     const int n = NT + j2;
     const int buf = n % NBUF;
-    const int gbuf = j2 % NBUF;
+    const int gbuf = j2 % NBUFG;
     int EaK = 0;
     if (k == 0) {
 #pragma unroll
@@ -273,7 +290,7 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
         }
       }
     }
-    if (j2 >= NBUF) mbar_wait(&S.gempty[gbuf], ((j2 / NBUF) - 1) & 1);
+    if (j2 >= NBUFG) mbar_wait(&S.gempty[gbuf], ((j2 / NBUFG) - 1) & 1);
     float* gt = S.gtile + gbuf * (kTT * Lpad) + lane * NS;
 #pragma unroll
     for (int ii = 0; ii < kTT; ++ii) {
@@ -308,23 +325,64 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
   }
 }
 
+// ============================================================================ TMA producer warp
+// One elected lane walks the sequence's rows tile by tile -- phase 1 upwards, phase 2 downwards (most recently
+// read rows first, so the re-read hits L2) -- and issues one bulk copy per row (the 16-byte aligned superset
+// of the 4-byte aligned row) into the shared-memory ring.  Phase-1 copies carry an L2 evict_last policy, phase-2
+// copies evict_first.
+__device__ __forceinline__ void producer_warp(const Problem& P, const FusedCfg& cfg, const Smem& S, int lane, int64_t b,
+                                              int Tb) {
+  if (lane != 0) return;
+  const int NT = (Tb + kTT - 1) / kTT;
+  const int total = (P.grad != nullptr) ? 2 * NT : NT;
+  const int C = (int)P.C;
+  const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  const uintptr_t safe_end = (reinterpret_cast<uintptr_t>(cfg.logits_end) + 15) & ~uintptr_t(15);
+  const bool end_unaligned = (reinterpret_cast<uintptr_t>(cfg.logits_end) & 15) != 0;
+  for (int n = 0; n < total; ++n) {
+    const int k = n < NT ? n : 2 * NT - 1 - n;
+    const int slot = n % cfg.NSLOT;
+    const int use = n / cfg.NSLOT;
+    if (use >= 1) mbar_wait(&S.sempty[slot], (use - 1) & 1);
+    const int nv = min(kTT, Tb - k * kTT);
+    unsigned char* dst = S.ring + (size_t)slot * kTT * cfg.RS;
+    const float* row0 = P.logits + ((int64_t)k * kTT * P.B + b) * C;
+    const int64_t strideT = P.B * (int64_t)C;
+    uint32_t bytes = 0;
+    for (int i = 0; i < nv; ++i) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(row0 + i * strideT);
+      const uintptr_t a0 = a & ~uintptr_t(15);
+      const uint32_t nb = (uint32_t)(((a + (uintptr_t)C * 4 + 15) & ~uintptr_t(15)) - a0);
+      // the very last row of an unaligned tensor would be over-read by < 16 bytes: copy it by hand instead
+      if (end_unaligned && a0 + nb == safe_end) {
+        const float* src = reinterpret_cast<const float*>(a);
+        float* d = reinterpret_cast<float*>(dst + (size_t)i * cfg.RS) + ((a >> 2) & 3);
+        for (int c = 0; c < C; ++c) d[c] = __ldg(src + c);
+      } else {
+        bytes += nb;
+      }
+    }
+    mbar_arrive_expect_tx(&S.sfull[slot], bytes);
+    const uint64_t pol = n < NT ? pol_keep : pol_stream;
+    for (int i = 0; i < nv; ++i) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(row0 + i * strideT);
+      const uintptr_t a0 = a & ~uintptr_t(15);
+      const uint32_t nb = (uint32_t)(((a + (uintptr_t)C * 4 + 15) & ~uintptr_t(15)) - a0);
+      if (!(end_unaligned && a0 + nb == safe_end))
+        bulk_g2s(dst + (size_t)i * cfg.RS, reinterpret_cast<const void*>(a0), nb, &S.sfull[slot], pol);
+    }
+  }
+}
+
 // ============================================================================ row warps
 // Geometry of one (t,b) row seen as 16-byte chunks: the row starts `off4` floats into chunk 0 and
-// ends `rem` floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0).
+// ends `rem` floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0).  `srow` is the row's
+// copy in the shared-memory ring (same 16-byte phase as in global memory).
 struct RowGeom {
-  const float* xrow;
-  const float4* base;  // chunk 0 (16-byte aligned), NOT offset by the lane
+  const float4* srow;
+  int64_t goff;        // element offset of the row in logits / grad
   int off4, nch, rem;  // rem in 1..4 = valid floats in the last chunk
 };
-__device__ __forceinline__ RowGeom row_geom(const float* row_ptr, int C) {
-  RowGeom g;
-  g.xrow = row_ptr;
-  g.off4 = (int)((reinterpret_cast<uintptr_t>(row_ptr) >> 2) & 3);
-  g.base = reinterpret_cast<const float4*>(row_ptr - g.off4);
-  g.nch = (g.off4 + C + 3) >> 2;
-  g.rem = g.off4 + C - 4 * (g.nch - 1);
-  return g;
-}
 __device__ __forceinline__ void mask_head(float4& v, int off4) {
   if (off4 > 0) v.x = kNegInf;
   if (off4 > 1) v.y = kNegInf;
@@ -351,35 +409,41 @@ struct Rows {
   const int lane, li, gi, wrow;
   const int64_t b;
   const int Tb, Lb, C;
-  const int64_t strideT;  // floats between rows t and t+1 of one sequence
   float* lse_arr;
-  const uint64_t pol_keep, pol_stream;
+  const uint64_t pol_stream;
   const float wgt;
+  const uintptr_t base_addr;
 
   __device__ __forceinline__ Rows(const Problem& P_, const FusedCfg& cfg_, const Smem& S_, int lane_, int wrow_,
                                   int64_t b_, int Tb_, int Lb_, float wgt_)
       : P(P_), cfg(cfg_), S(S_), lane(lane_), li(lane_ & (LPR - 1)), gi(lane_ / LPR), wrow(wrow_), b(b_), Tb(Tb_),
-        Lb(Lb_), C((int)P_.C), strideT(P_.B * P_.C),
-        lse_arr(cfg_.lse_global ? cfg_.ws_lse + (size_t)b_ * P_.T : S_.lse), pol_keep(policy_evict_last()),
-        pol_stream(policy_evict_first()), wgt(wgt_) {}
+        Lb(Lb_), C((int)P_.C), lse_arr(cfg_.lse_global ? cfg_.ws_lse + (size_t)b_ * P_.T : S_.lse),
+        pol_stream(policy_evict_first()), wgt(wgt_), base_addr(reinterpret_cast<uintptr_t>(P_.logits)) {}
 
-  __device__ __forceinline__ const float* row_ptr(int t) const { return P.logits + ((int64_t)t * P.B + b) * C; }
+  // row t of this sequence; `slot_rows` = start of the ring slot holding the tile, i = row inside the tile
+  __device__ __forceinline__ RowGeom geom(int t, const unsigned char* slot_rows, int i) const {
+    RowGeom g;
+    g.goff = ((int64_t)t * P.B + b) * C;
+    g.off4 = (int)(((base_addr >> 2) + (uintptr_t)g.goff) & 3);
+    g.nch = (g.off4 + C + 3) >> 2;
+    g.rem = g.off4 + C - 4 * (g.nch - 1);
+    g.srow = reinterpret_cast<const float4*>(slot_rows + (size_t)i * cfg.RS);
+    return g;
+  }
 
-  template <bool kFirstSeg, bool kLastSeg>
-  __device__ __forceinline__ void load_seg(const RowGeom& g, bool act, int seg, uint64_t pol, float4 (&v)[CPL]) const {
-    const float4* src = g.base + seg * SEG + li;
+  __device__ __forceinline__ void load_seg(const RowGeom& g, bool act, int seg, float4 (&v)[CPL]) const {
+    const float4* src = g.srow + seg * SEG + li;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int q = seg * SEG + li + c * LPR;
-      const bool in = kLastSeg ? (act && q < g.nch) : act;
-      v[c] = in ? ldg_f4_hint(src + c * LPR, pol) : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+      v[c] = (act && q < g.nch) ? src[c * LPR] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
     }
   }
   // elements of the neighbouring rows (head of chunk 0 / tail of chunk nch-1) -> -inf
-  template <bool kFirstSeg, bool kLastSeg, bool kSingle>
-  __device__ __forceinline__ void mask_seg(const RowGeom& g, int seg, float4 (&v)[CPL]) const {
-    if (kFirstSeg && li == 0) mask_head(v[0], g.off4);
-    if (kLastSeg) {
+  template <bool kSingle>
+  __device__ __forceinline__ void mask_seg(const RowGeom& g, int seg, bool first, bool last, float4 (&v)[CPL]) const {
+    if (first && li == 0) mask_head(v[0], g.off4);
+    if (last) {
       const int ql = g.nch - 1 - seg * SEG - li;  // tail chunk sits in slot c with c*LPR == ql
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
@@ -420,88 +484,58 @@ struct Rows {
     }
   }
 
-  // emissions p_t(s) = softmax(x_t)[label_s] for the R rows of pass `pr` of tile k -> p-tile
-  __device__ __forceinline__ void emit_issue(int k, int pr, int nv, float (&xg)[NSL]) const {
-    const int i = pr * R + gi;
-    const float* xrow = row_ptr(k * kTT + i);
-#pragma unroll
-    for (int j = 0; j < NSL; ++j) {
-      const int st = li + j * LPR;
-      xg[j] = (i < nv && st < Lb) ? __ldg(xrow + S.lab[st]) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void emit_finish(int pr, int nv, float lse, const float (&xg)[NSL], float* ptile_buf) const {
-    const int i = pr * R + gi;
-    if (i < nv) {
+  // emissions p_t(s) = softmax(x_t)[label_s] for row i (gathered from the row's shared-memory copy) -> p-tile
+  __device__ __forceinline__ void emit_row(const RowGeom& g, bool act, int i, float lse, float* ptile_buf) const {
+    if (act) {
+      const float* xr = reinterpret_cast<const float*>(g.srow) + g.off4;
       const float lb2 = lse * kLog2e;
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int st = li + j * LPR;
-        const float pv = (st < Lb) ? fmaxf(ex2f(fmaf(xg[j], kLog2e, -lb2)), kPMin) : 0.f;
+        float pv = 0.f;
+        if (st < Lb) pv = fmaxf(ex2f(fmaf(xr[S.lab[st]], kLog2e, -lb2)), kPMin);
         ptile_buf[i * Lpad + st] = pv;
       }
     }
   }
 
   // ---------------------------------------------------------------- phase 1: one tile
-  __device__ __forceinline__ void forward_tile(int k, int nv, float* ptile_buf) const {
-    if (cfg.NSEG == 1) {
-      RowGeom g[NP];
-      float4 v[NP][CPL];
+  __device__ __forceinline__ void forward_tile(int k, int nv, const unsigned char* slot_rows, float* ptile_buf) const {
 #pragma unroll
-      for (int pr = 0; pr < NP; ++pr) {  // all loads of the tile in flight before any use
-        const int i = pr * R + gi;
-        g[pr] = row_geom(row_ptr(k * kTT + i), C);
-        load_seg<true, true>(g[pr], i < nv, 0, pol_keep, v[pr]);
-      }
-#pragma unroll
-      for (int pr = 0; pr < NP; ++pr) {
-        const int i = pr * R + gi;
-        mask_seg<true, true, true>(g[pr], 0, v[pr]);
-        float m_run = kNegInf, s_run = 0.f;
-        seg_max_sum(v[pr], m_run, s_run);
-        float xg[NSL];
-        emit_issue(k, pr, nv, xg);  // L1 hits: the row was just read by this group
-        const float m = group_max(m_run);
-        const float s = group_sum(m_run > kNegInf ? s_run * ex2f((m_run - m) * kLog2e) : 0.f);
-        const float lse = m + logf(s);
-        if (i < nv && li == 0) lse_arr[k * kTT + i] = lse;
-        emit_finish(pr, nv, lse, xg, ptile_buf);
-      }
-    } else {
-#pragma unroll 1
-      for (int pr = 0; pr < NP; ++pr) {
-        const int i = pr * R + gi;
-        const RowGeom g = row_geom(row_ptr(k * kTT + i), C);
-        float m_run = kNegInf, s_run = 0.f;
+    for (int pr = 0; pr < NP; ++pr) {
+      const int i = pr * R + gi;
+      const bool act = i < nv;
+      const RowGeom g = geom(k * kTT + i, slot_rows, i);
+      float m_run = kNegInf, s_run = 0.f;
+      if (cfg.NSEG == 1) {
+        float4 v[CPL];
+        load_seg(g, act, 0, v);
+        mask_seg<true>(g, 0, true, true, v);
+        seg_max_sum(v, m_run, s_run);
+      } else {
         for (int seg = 0; seg < cfg.NSEG; ++seg) {
           float4 v[CPL];
-          load_seg<true, true>(g, i < nv, seg, pol_keep, v);
-          if (seg == 0 && li == 0) mask_head(v[0], g.off4);
-          if (seg == cfg.NSEG - 1) mask_seg<false, true, false>(g, seg, v);
+          load_seg(g, act, seg, v);
+          mask_seg<false>(g, seg, seg == 0, seg == cfg.NSEG - 1, v);
           seg_max_sum(v, m_run, s_run);
         }
-        float xg[NSL];
-        emit_issue(k, pr, nv, xg);
-        const float m = group_max(m_run);
-        const float s = group_sum(m_run > kNegInf ? s_run * ex2f((m_run - m) * kLog2e) : 0.f);
-        const float lse = m + logf(s);
-        if (i < nv && li == 0) lse_arr[k * kTT + i] = lse;
-        emit_finish(pr, nv, lse, xg, ptile_buf);
       }
+      const float m = group_max(m_run);
+      const float s = group_sum(m_run > kNegInf ? s_run * ex2f((m_run - m) * kLog2e) : 0.f);
+      const float lse = m + logf(s);
+      if (act && li == 0) lse_arr[k * kTT + i] = lse;
+      emit_row(g, act, i, lse, ptile_buf);
     }
   }
 
   // ---------------------------------------------------------------- phase 2 stage A: emissions again
-  __device__ __forceinline__ void emit_tile(int k, int nv, float* ptile_buf) const {
-    float xg[NP][NSL];
-#pragma unroll
-    for (int pr = 0; pr < NP; ++pr) emit_issue(k, pr, nv, xg[pr]);
+  __device__ __forceinline__ void emit_tile(int k, int nv, const unsigned char* slot_rows, float* ptile_buf) const {
 #pragma unroll
     for (int pr = 0; pr < NP; ++pr) {
       const int i = pr * R + gi;
-      const float lse = (i < nv) ? lse_arr[k * kTT + i] : 0.f;
-      emit_finish(pr, nv, lse, xg[pr], ptile_buf);
+      const bool act = i < nv;
+      const RowGeom g = geom(k * kTT + i, slot_rows, i);
+      emit_row(g, act, i, act ? lse_arr[k * kTT + i] : 0.f, ptile_buf);
     }
   }
 
@@ -529,15 +563,17 @@ struct Rows {
     }
   }
   __device__ __forceinline__ void grad_seg(const float4* d4, const RowGeom& g, int seg, float lb2, float4 (&v)[CPL]) const {
+    const float4* src = g.srow + seg * SEG + li;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int q = seg * SEG + li + c * LPR;
       if (q < g.nch) {
+        const float4 x = src[c * LPR];
         const float4 d = d4[q];
-        v[c].x = fmaf(ex2f(fmaf(v[c].x, kLog2e, -lb2)), wgt, -d.x);
-        v[c].y = fmaf(ex2f(fmaf(v[c].y, kLog2e, -lb2)), wgt, -d.y);
-        v[c].z = fmaf(ex2f(fmaf(v[c].z, kLog2e, -lb2)), wgt, -d.z);
-        v[c].w = fmaf(ex2f(fmaf(v[c].w, kLog2e, -lb2)), wgt, -d.w);
+        v[c].x = fmaf(ex2f(fmaf(x.x, kLog2e, -lb2)), wgt, -d.x);
+        v[c].y = fmaf(ex2f(fmaf(x.y, kLog2e, -lb2)), wgt, -d.y);
+        v[c].z = fmaf(ex2f(fmaf(x.z, kLog2e, -lb2)), wgt, -d.z);
+        v[c].w = fmaf(ex2f(fmaf(x.w, kLog2e, -lb2)), wgt, -d.w);
       }
     }
   }
@@ -561,56 +597,28 @@ struct Rows {
   }
 
   // ---------------------------------------------------------------- phase 2 stage B: one tile
-  // The row loads do not depend on the chain, so they are issued before waiting for gamma.
-  template <typename WaitFn>
-  __device__ __forceinline__ void backward_tile(int k, int nv, const float* gtile_buf, WaitFn wait_gamma) const {
+  __device__ __forceinline__ void backward_tile(int k, int nv, const unsigned char* slot_rows, const float* gtile_buf) const {
     float* dl = S.delta + (wrow * R + gi) * cfg.Cd;
     const float4* d4 = reinterpret_cast<const float4*>(dl);
-    if (cfg.NSEG == 1) {
-      RowGeom g[NP];
-      float4 v[NP][CPL];
 #pragma unroll
-      for (int pr = 0; pr < NP; ++pr) {
-        const int i = pr * R + gi;
-        g[pr] = row_geom(row_ptr(k * kTT + i), C);
-        load_seg<true, true>(g[pr], i < nv, 0, pol_stream, v[pr]);
-      }
-      wait_gamma();
-#pragma unroll
-      for (int pr = 0; pr < NP; ++pr) {
-        const int i = pr * R + gi;
-        const bool act = i < nv;
-        scatter_add(dl, g[pr], act, i, gtile_buf);
-        __syncwarp();
-        if (act) grad_seg(d4, g[pr], 0, lse_arr[k * kTT + i] * kLog2e, v[pr]);
-        __syncwarp();
-        scatter_clear(dl, g[pr], act);
-        if (act) store_seg(P.grad + (g[pr].xrow - P.logits), g[pr], 0, v[pr]);
-        __syncwarp();
-      }
-    } else {
-      wait_gamma();
-#pragma unroll 1
-      for (int pr = 0; pr < NP; ++pr) {
-        const int i = pr * R + gi;
-        const bool act = i < nv;
-        const RowGeom g = row_geom(row_ptr(k * kTT + i), C);
-        scatter_add(dl, g, act, i, gtile_buf);
-        __syncwarp();
-        if (act) {
-          const float lb2 = lse_arr[k * kTT + i] * kLog2e;
-          float* grow = P.grad + (g.xrow - P.logits);
-          for (int seg = 0; seg < cfg.NSEG; ++seg) {
-            float4 v[CPL];
-            load_seg<true, true>(g, true, seg, pol_stream, v);
-            grad_seg(d4, g, seg, lb2, v);
-            store_seg(grow, g, seg, v);
-          }
+    for (int pr = 0; pr < NP; ++pr) {
+      const int i = pr * R + gi;
+      const bool act = i < nv;
+      const RowGeom g = geom(k * kTT + i, slot_rows, i);
+      scatter_add(dl, g, act, i, gtile_buf);
+      __syncwarp();
+      if (act) {
+        const float lb2 = lse_arr[k * kTT + i] * kLog2e;
+        float* grow = P.grad + g.goff;
+        for (int seg = 0; seg < cfg.NSEG; ++seg) {
+          float4 v[CPL];
+          grad_seg(d4, g, seg, lb2, v);
+          store_seg(grow, g, seg, v);
         }
-        __syncwarp();
-        scatter_clear(dl, g, act);
-        __syncwarp();
       }
+      __syncwarp();
+      scatter_clear(dl, g, act);
+      __syncwarp();
     }
   }
 
@@ -620,69 +628,65 @@ struct Rows {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t t = (int64_t)t_begin + wrow * R + gi; t < P.T; t += kNW * R) {
-      const RowGeom g = row_geom(row_ptr((int)t), C);
-      float* grow = P.grad + (g.xrow - P.logits);
-      for (int seg = 0; seg < cfg.NSEG; ++seg) store_seg(grow, g, seg, z);
+      const RowGeom g = geom((int)t, nullptr, 0);
+      for (int seg = 0; seg < cfg.NSEG; ++seg) store_seg(P.grad + g.goff, g, seg, z);
     }
   }
 
   __device__ __forceinline__ void run() const {
     const int NT = (Tb + kTT - 1) / kTT;
-    const int NBUF = cfg.NBUF;
+    const int NBUF = cfg.NBUFP, NBUFG = cfg.NBUFG, NSLOT = cfg.NSLOT;
+    const size_t slot_bytes = (size_t)kTT * cfg.RS;
     // ---- phase 1: tiles k = wrow, wrow+NW, ...
     for (int k = wrow; k < NT; k += kNW) {
       const int buf = k % NBUF;
+      const int slot = k % NSLOT;
       if (k >= NBUF) mbar_wait(&S.pempty[buf], ((k / NBUF) - 1) & 1);
-      forward_tile(k, min(kTT, Tb - k * kTT), S.ptile + buf * (kTT * Lpad));
+      mbar_wait(&S.sfull[slot], (k / NSLOT) & 1);
+      forward_tile(k, min(kTT, Tb - k * kTT), S.ring + slot * slot_bytes, S.ptile + buf * (kTT * Lpad));
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.pfull[buf]);
+      if (lane == 0) {
+        mbar_arrive(&S.pfull[buf]);
+        mbar_arrive(&S.sempty[slot]);
+      }
     }
     if (P.grad == nullptr) return;
     if (Tb < P.T) zero_rows(Tb);
-    // ---- phase 2: the same warp owns the same tiles (it wrote their lse values), walked downwards.
-    // Order per warp: A(k0), A(k0-NW), B(k0), A(k0-2NW), B(k0-NW), ... so the chain always has a tile ahead.
-    int kA = NT - 1 - ((NT - 1 - wrow) % kNW + kNW) % kNW;  // largest k <= NT-1 with k % NW == wrow
-    if (kA > NT - 1 || kA < 0) kA = -1;
-    int kB = kA;
-    auto stage_a = [&](int k) {
-      const int n = NT + (NT - 1 - k);
-      const int buf = n % NBUF;
+    // ---- phase 2: the same warp owns the same tiles (it wrote their lse values), walked downwards:
+    // A(k) = emissions -> chain, B(k) = gradient rows once the chain has produced gamma(k).
+    int k = NT - 1 - ((NT - 1 - wrow) % kNW + kNW) % kNW;  // largest k <= NT-1 with k % NW == wrow
+    for (; k >= 0; k -= kNW) {
+      const int j2 = NT - 1 - k;
+      const int n = NT + j2;
+      const int buf = n % NBUF, gbuf = j2 % NBUFG, slot = n % NSLOT;
+      const int nv = min(kTT, Tb - k * kTT);
+      const unsigned char* rows = S.ring + slot * slot_bytes;
       if (n >= NBUF) mbar_wait(&S.pempty[buf], ((n / NBUF) - 1) & 1);
-      emit_tile(k, min(kTT, Tb - k * kTT), S.ptile + buf * (kTT * Lpad));
+      mbar_wait(&S.sfull[slot], (n / NSLOT) & 1);
+      emit_tile(k, nv, rows, S.ptile + buf * (kTT * Lpad));
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.pfull[buf]);
-    };
-    auto stage_b = [&](int k) {
-      const int j2 = NT - 1 - k;
-      const int gbuf = j2 % NBUF;
-      backward_tile(k, min(kTT, Tb - k * kTT), S.gtile + gbuf * (kTT * Lpad),
-                    [&]() { mbar_wait(&S.gfull[gbuf], (j2 / NBUF) & 1); });
-      if (lane == 0) mbar_arrive(&S.gempty[gbuf]);
-    };
-    if (kA >= 0) {
-      stage_a(kA);
-      kA -= kNW;
-    }
-    while (kB >= 0) {
-      if (kA >= 0) {
-        stage_a(kA);
-        kA -= kNW;
+      mbar_wait(&S.gfull[gbuf], (j2 / NBUFG) & 1);
+      backward_tile(k, nv, rows, S.gtile + gbuf * (kTT * Lpad));
+      if (lane == 0) {
+        mbar_arrive(&S.gempty[gbuf]);
+        mbar_arrive(&S.sempty[slot]);
       }
-      stage_b(kB);
-      kB -= kNW;
     }
   }
 };
 
 // ============================================================================ kernel
 template <int NS, int LPR, int CPL>
-__global__ void __launch_bounds__(32 * (1 + kNW), 3) nbctc_fused_kernel(const Problem P, const FusedCfg cfg) {
+__global__ void __launch_bounds__(kThreads, 3) nbctc_fused_kernel(const Problem P, const FusedCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem S;
   S.pfull = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar);
   S.pempty = S.pfull + kMaxBuf;
   S.gfull = S.pempty + kMaxBuf;
   S.gempty = S.gfull + kMaxBuf;
+  S.sfull = S.gempty + kMaxBuf;
+  S.sempty = S.sfull + kMaxSlot;
   S.lab = reinterpret_cast<int*>(smem_raw + cfg.o_lab);
   S.lse = reinterpret_cast<float*>(smem_raw + cfg.o_lse);
   S.ckpt = reinterpret_cast<double*>(smem_raw + cfg.o_ckpt);
@@ -691,6 +695,7 @@ __global__ void __launch_bounds__(32 * (1 + kNW), 3) nbctc_fused_kernel(const Pr
   S.gtile = reinterpret_cast<float*>(smem_raw + cfg.o_gtile);
   S.atile = reinterpret_cast<double*>(smem_raw + cfg.o_atile);
   S.delta = reinterpret_cast<float*>(smem_raw + cfg.o_delta);
+  S.ring = smem_raw + cfg.o_ring;
 
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -714,17 +719,22 @@ __global__ void __launch_bounds__(32 * (1 + kNW), 3) nbctc_fused_kernel(const Pr
     mbar_init(&S.gfull[tid], 1);
     mbar_init(&S.gempty[tid], 1);
   }
+  if (tid < kMaxSlot) {
+    mbar_init(&S.sfull[tid], 1);
+    mbar_init(&S.sempty[tid], 1);
+  }
   {
     const int nd = kNW * (32 / LPR) * cfg.Cd;
     for (int i = tid; i < nd; i += blockDim.x) S.delta[i] = 0.f;
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   bad = __syncthreads_or(bad);
   ok = ok && !bad;
   const float wgt = P.w_scalar * (P.seq_w ? P.seq_w[b] : 1.f);
   if (!ok) {
     if (tid == 0) P.loss[b] = INFINITY;
-    if (P.grad != nullptr && warp > 0) {
+    if (P.grad != nullptr && warp >= 1 && warp <= kNW) {
       Rows<NS, LPR, CPL> rows(P, cfg, S, lane, warp - 1, b, 0, 0, wgt);
       rows.zero_rows(0);
     }
@@ -732,9 +742,11 @@ __global__ void __launch_bounds__(32 * (1 + kNW), 3) nbctc_fused_kernel(const Pr
   }
   if (warp == 0) {
     chain_warp<NS>(P, cfg, S, lane, b, Tb, Lb, wgt);
-  } else {
+  } else if (warp <= kNW) {
     Rows<NS, LPR, CPL> rows(P, cfg, S, lane, warp - 1, b, Tb, Lb, wgt);
     rows.run();
+  } else {
+    producer_warp(P, cfg, S, lane, b, Tb);
   }
 }
 
@@ -743,7 +755,8 @@ int launch_inst(const Problem& p, const FusedCfg& cfg, cudaStream_t stream) {
   auto kern = nbctc_fused_kernel<NS, LPR, CPL>;
   if (cfg.smem_bytes > 48 * 1024)
     NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes));
-  kern<<<(unsigned)p.B, 32 * (1 + kNW), cfg.smem_bytes, stream>>>(p, cfg);
+  NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<(unsigned)p.B, kThreads, cfg.smem_bytes, stream>>>(p, cfg);
   NBCTC_LAUNCH_CHECK();
   return NBCTC_OK;
 }
@@ -765,6 +778,13 @@ int launch_ns(const Problem& p, const FusedCfg& cfg, cudaStream_t stream) {
       case 6: return launch_inst<NS, 8, 6>(p, cfg, stream);
       case 7: return launch_inst<NS, 8, 7>(p, cfg, stream);
       case 8: return launch_inst<NS, 8, 8>(p, cfg, stream);
+    }
+  } else if (cfg.LPR == 32) {
+    switch (cfg.CPL) {
+      case 3: return launch_inst<NS, 32, 3>(p, cfg, stream);
+      case 4: return launch_inst<NS, 32, 4>(p, cfg, stream);
+      case 6: return launch_inst<NS, 32, 6>(p, cfg, stream);
+      case 8: return launch_inst<NS, 32, 8>(p, cfg, stream);
     }
   }
   set_error("no fused kernel instance for LPR=%d CPL=%d", cfg.LPR, cfg.CPL);

@@ -46,38 +46,43 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax, const void* logits
     c.LPR = 8;
     c.CPL = (int)std::max<int64_t>(3, (nch + 7) / 8);
   } else {
-    c.LPR = 8;
-    c.CPL = 8;
-    c.NSEG = (int)((nch + 63) / 64);
+    // long rows: one row per warp pass (a single scatter buffer per warp), 32 lanes x CPL chunks per segment
+    c.LPR = 32;
+    c.CPL = nch <= 96 ? 3 : nch <= 128 ? 4 : nch <= 192 ? 6 : 8;
+    c.NSEG = (int)((nch + 32 * c.CPL - 1) / (32 * c.CPL));
   }
+  c.RS = (int)(16 * nch);
+  c.logits_end = nullptr;
   c.NTmax = (int)((T + kTT - 1) / kTT);
   c.Cd = (int)((C + 3 + 3) / 4 * 4 + 4);
   const size_t budget = 200 * 1024;
-  auto layout = [&](int nbuf, bool ck_glob, bool lse_glob) {
+  auto layout = [&](int nslot, bool ck_glob, bool lse_glob) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
-    c.NBUF = nbuf; c.ckpt_global = ck_glob; c.lse_global = lse_glob;
-    c.o_bar = take(sizeof(uint64_t) * 4 * kMaxBuf);
+    c.NSLOT = nslot; c.NBUFP = 2 * kNW; c.NBUFG = kNW; c.ckpt_global = ck_glob; c.lse_global = lse_glob;
+    const int nbuf = c.NBUFP;
+    c.o_bar = take(sizeof(uint64_t) * (4 * kMaxBuf + 2 * kMaxSlot));
     c.o_lab = take(sizeof(int) * c.Lpad);
     c.o_lse = take(lse_glob ? 16 : sizeof(float) * T);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)c.NTmax * c.Lpad);
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)c.NTmax);
     c.o_ptile = take(sizeof(float) * (size_t)nbuf * kTT * c.Lpad);
-    c.o_gtile = take(sizeof(float) * (size_t)nbuf * kTT * c.Lpad);
+    c.o_gtile = take(sizeof(float) * (size_t)c.NBUFG * kTT * c.Lpad);
     c.o_atile = take(c.NS <= 2 ? 16 : sizeof(double) * (size_t)kTT * c.Lpad);
     c.o_delta = take(sizeof(float) * (size_t)kNW * (32 / c.LPR) * c.Cd);
+    off = align_up(off, 128);
+    c.o_ring = take((size_t)nslot * kTT * c.RS);
     c.smem_bytes = (uint32_t)off;
     return off;
   };
-  // prefer everything in shared memory while a CTA stays small enough for >= 4 CTAs per SM
+  // pass 0: everything in shared memory and <= 74 KB so that 3 CTAs share an SM; later passes move the
+  // checkpoints / row constants to the workspace and let one CTA take up to ~200 KB.
   bool placed = false;
   for (int pass = 0; pass < 3 && !placed; ++pass) {
     const bool ckg = pass >= 1, lsg = pass >= 2;
-    const size_t cap = (pass == 0) ? 56 * 1024 : budget;
-    for (int nbuf = 2 * kNW; nbuf >= kNW + 1 && !placed; --nbuf) {
-      if (layout(nbuf, ckg, lsg) <= cap) placed = true;
-      if (pass == 0) break;
-    }
+    const size_t cap = (pass == 0) ? 74 * 1024 : budget;
+    for (int nslot = (pass == 0 ? 7 : 6); nslot >= 3 && !placed; --nslot)
+      if (layout(nslot, ckg, lsg) <= cap) placed = true;
   }
   if (!placed) return pl;
   pl.ok = true;
@@ -135,6 +140,7 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
     off = align_up(off + sizeof(int) * (size_t)p.B * pl.cfg.NTmax, 256);
   }
   if (pl.cfg.lse_global) pl.cfg.ws_lse = reinterpret_cast<float*>(w + off);
+  pl.cfg.logits_end = p.logits + p.T * p.B * p.C;
   switch (pl.cfg.NS) {
     case 1: return launch_fused_ns1(p, pl.cfg, stream);
     case 2: return launch_fused_ns2(p, pl.cfg, stream);
