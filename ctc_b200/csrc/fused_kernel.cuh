@@ -1,12 +1,16 @@
-// Fused no-blank CTC forward+backward kernel for sm_100a (see nbctc_fused.cu for the overview).
+// Fused no-blank CTC forward+backward kernel for sm_100a (overview in nbctc_fused.cu).
 //
-// One CTA per sequence b, warp-specialised:
-//   warp 0      "chain" warp: lattice recursions, lane = NS consecutive states (NoBlankCTC.py:71-87)
-//   warps 1..NW "row" warps : stream (t,b) rows of the logits, LPR lanes per row, CPL 16-byte chunks per lane
-// Template parameters fix the row geometry at compile time so the streaming code is branch-light:
-//   NS  states per chain lane (1,2,4,8  -> Lmax <= 32*NS)
-//   LPR lanes per row (4 or 8), R = 32/LPR rows per warp pass, kTT/R passes per tile
-//   CPL chunks per lane per row segment
+// One CTA per sequence b, warp-specialised, all hand-offs through shared memory + mbarriers:
+//   warp 0        chain warp.  16 lanes x NS states hold the lattice state in float64 (linear domain, exact
+//                 power-of-two rescaling per tile).  Lanes 0-15 run alpha; in phase 2 lanes 16-31 run the beta
+//                 recursion IN THE SAME INSTRUCTIONS (beta is stored in reversed state order so both halves shift
+//                 the same way), while lanes 0-15 replay alpha inside the tile from the phase-1 checkpoint.
+//   warps 1..NW   row warps.  LPR lanes per (t,b) row, CPL 16-byte chunks per lane: row log-partition + emission
+//                 gather (phase 1), softmax - scatter(gamma) and 128-bit streaming stores (phase 2).
+//   warp NW+1     TMA producer.  One lane issues cp.async.bulk copies of the rows (16-byte aligned superset of the
+//                 4-byte aligned rows) into a shared-memory ring: phase 1 upwards with an L2 evict_last policy,
+//                 phase 2 downwards (most recently read rows first -> L2 hits) with evict_first.
+// Template parameters: NS (chain states per lane, Lmax <= 16*NS), LPR, CPL (row geometry).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -22,26 +26,25 @@ constexpr int kNW = 4;        // row warps per CTA
 constexpr int kThreads = 32 * (kNW + 2);  // chain warp + row warps + TMA producer warp
 
 struct FusedCfg {
-  int NS, Lpad;
+  int NS, Lpad;      // chain: NS states per lane, 16 lanes per direction, Lpad = 16*NS
   int LPR, CPL, NSEG;
-  int NBUFP, NBUFG; // p-tile / gamma-tile ring depths
-  int NSLOT;        // row-tile ring depth (TMA bulk copies land here)
-  int RS;           // bytes per row slot = 16 * max chunks per row
-  int NTmax;        // ceil(T / kTT)
-  int Cd;           // floats per scatter buffer
-  int ckpt_global;  // checkpoints live in the workspace instead of shared memory
+  int NBUFP, NBUFG;  // p-tile / gamma-tile ring depths
+  int NSLOT;         // row-tile ring depth (TMA bulk copies land here)
+  int RS;            // bytes per row slot = 16 * max chunks per row
+  int NTmax;         // ceil(T / kTT)
+  int ckpt_global;   // checkpoints live in the workspace instead of shared memory
   int lse_global;
-  uint32_t o_bar, o_lab, o_lse, o_ckpt, o_cke, o_ptile, o_gtile, o_atile, o_delta, o_ring, smem_bytes;
-  double* ws_ckpt;  // [B][NTmax][Lpad]
-  int* ws_cke;      // [B][NTmax]
-  float* ws_lse;    // [B][T]
+  uint32_t o_bar, o_lab, o_lse, o_ckpt, o_cke, o_ptile, o_gtile, o_abtile, o_ring, smem_bytes;
+  double* ws_ckpt;   // [B][NTmax][Lpad]
+  int* ws_cke;       // [B][NTmax]
+  float* ws_lse;     // [B][T]
   const float* logits_end;  // one past the last logit (bulk copies never read past its 16-byte round-up)
 };
 
-int launch_fused_ns1(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
 int launch_fused_ns2(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
 int launch_fused_ns4(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
 int launch_fused_ns8(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
+int launch_fused_ns16(const Problem& p, const FusedCfg& cfg, cudaStream_t stream);
 
 #ifdef __CUDACC__
 namespace fused {
@@ -61,26 +64,64 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-// TMA bulk copy global -> shared (1-D, 16-byte aligned, size multiple of 16), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-      : "memory");
-}
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "NBCTC_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-      "@P1 bra NBCTC_DONE;\n"
-      "bra NBCTC_WAIT;\n"
-      "NBCTC_DONE:\n"
-      "}\n" ::"r"(smem_u32(b)),
-      "r"(parity), "r"(2000000u)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// Wait for the phase with the given parity.  A protocol bug would otherwise hang the GPU: after ~2 s of polling
+// the kernel traps instead (the host sees a launch failure), which is never reached in a correct run.
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t bar = smem_u32(b);
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      printf("nbctc: mbarrier wait timed out (block %d warp %d bar+%u parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+             bar, parity);
+      __trap();
+    }
+  }
+}
+// Monotonic shared-memory counters guard the rings that have several waiting warps: an mbarrier parity wait is only
+// sound while the waiter is at most one phase ahead of the barrier, which a warp that skips ahead in the tile order
+// (phase-1 -> phase-2 hand-over) cannot guarantee.  Publisher: fence + store; waiter: spin + fence.
+__device__ __forceinline__ void count_publish(volatile int* c, int v) {
+  __threadfence_block();
+  *c = v;
+}
+__device__ __forceinline__ void count_wait(volatile int* c, int target) {
+  if (*c >= target) { __threadfence_block(); return; }
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*c < target) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      printf("nbctc: counter wait timed out (block %d warp %d target %d have %d)\n", (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), target, *c);
+      __trap();
+    }
+  }
+  __threadfence_block();
+}
+// TMA bulk copy global -> shared (1-D, 16-byte aligned, size multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, uint64_t src_gmem, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {
@@ -98,13 +139,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(pol));
-  return v;
-}
 __device__ __forceinline__ void stg_f4_hint(float4* ptr, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol)
@@ -113,273 +147,240 @@ __device__ __forceinline__ void stg_f4_hint(float4* ptr, float4 v, uint64_t pol)
 __device__ __forceinline__ void stg_f_hint(float* ptr, float v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
 }
-
-template <int NS>
-__device__ __forceinline__ int rescale_pow2(double (&v)[NS]) {
-  double m = v[0];
-#pragma unroll
-  for (int j = 1; j < NS; ++j) m = fmax(m, v[j]);
-  unsigned hi = (unsigned)__double2hiint(m);  // values are >= 0
-  unsigned mx = __reduce_max_sync(0xffffffffu, hi);
-  int ex = (int)(mx >> 20);
-  if (ex == 0 || ex >= 0x7ff) return 0;
-  int e = ex - 1023;
-  double sc = __hiloint2double((1023 - e) << 20, 0);  // exact 2^-e
-#pragma unroll
-  for (int j = 0; j < NS; ++j) v[j] *= sc;
-  return e;
-}
 __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the normal range
   e = max(-1022, min(1023, e));
   return __hiloint2double((1023 + e) << 20, 0);
 }
 
 struct Smem {
-  uint64_t *pfull, *pempty, *gfull, *gempty, *sfull, *sempty;
-  unsigned char* ring;
+  uint64_t *pfull, *gfull, *gempty, *sfull, *sempty;
+  volatile int* cnt;  // [0] p-tiles consumed by the chain, [1] row tiles issued by the producer (monotonic)
   int* lab;
   float* lse;
   double* ckpt;
   int* cke;
   float* ptile;
   float* gtile;
-  double* atile;
-  float* delta;
+  double* abtile;
+  unsigned char* ring;
 };
 
 // ============================================================================ chain warp
+// rescale the NS states of each 16-lane half by the exact power of two of the half's largest value
 template <int NS>
-__device__ __forceinline__ void load_p(const float* src, double (&p)[NS]) {
-  if constexpr (NS == 1) {
-    p[0] = (double)src[0];
-  } else if constexpr (NS == 2) {
-    float2 v = *reinterpret_cast<const float2*>(src);
-    p[0] = v.x; p[1] = v.y;
+__device__ __forceinline__ int rescale_half(double (&v)[NS]) {
+  double m = v[0];
+#pragma unroll
+  for (int j = 1; j < NS; ++j) m = fmax(m, v[j]);
+  int hi = __double2hiint(m);  // values are >= 0, so the high word orders like the value
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  const int ex = hi >> 20;
+  if (ex == 0 || ex >= 0x7ff) return 0;
+  const int e = ex - 1023;
+  const double sc = __hiloint2double((1023 - e) << 20, 0);  // exact 2^-e
+#pragma unroll
+  for (int j = 0; j < NS; ++j) v[j] *= sc;
+  return e;
+}
+
+// emissions of the lane's NS states for one row of a p-tile; the beta half reads them in reversed state order
+template <int NS>
+__device__ __forceinline__ void load_p(const float* row, int hl, bool rev, double (&p)[NS]) {
+  const float* src = row + (rev ? (16 - 1 - hl) * NS : hl * NS);
+  float t[NS];
+  if constexpr (NS == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(src);
+    t[0] = v.x; t[1] = v.y;
   } else {
 #pragma unroll
     for (int j = 0; j < NS; j += 4) {
-      float4 v = *reinterpret_cast<const float4*>(src + j);
-      p[j] = v.x; p[j + 1] = v.y; p[j + 2] = v.z; p[j + 3] = v.w;
+      const float4 v = *reinterpret_cast<const float4*>(src + j);
+      t[j] = v.x; t[j + 1] = v.y; t[j + 2] = v.z; t[j + 3] = v.w;
     }
   }
-}
-template <int NS>
-__device__ __forceinline__ void store_g(float* dst, const float (&g)[NS]) {
-  if constexpr (NS == 1) {
-    dst[0] = g[0];
-  } else if constexpr (NS == 2) {
-    *reinterpret_cast<float2*>(dst) = make_float2(g[0], g[1]);
-  } else {
 #pragma unroll
-    for (int j = 0; j < NS; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-  }
+  for (int j = 0; j < NS; ++j) p[j] = (double)(rev ? t[NS - 1 - j] : t[j]);
 }
 
-// alpha_t(s) = (alpha_{t-1}(s) + alpha_{t-1}(s-1)) * p_t(s); `carry` enters state 0 (1.0 only at t = 0: the
-// virtual start state, NoBlankCTC.py:92-93 forward_prob[:,0] = 0 and the t>0 shift guard :75)
+// x(s) <- (x(s) + x(s-1)) * p(s) in the lane's (possibly reversed) state order; `sum` keeps the pre-emission value.
+// alpha: x = alpha (NoBlankCTC.py:73-85).  beta half: x(s) = beta_t(s) p_t(s), sum = beta_t(s).
+// `carry` enters position 0 of the half (the virtual start state: NoBlankCTC.py:92-93 and the t>0 guard at :75).
 template <int NS>
-__device__ __forceinline__ void alpha_step(double (&a)[NS], const double (&p)[NS], int lane, double& carry) {
-  double up = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
-  if (lane == 0) up = carry;
+__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double& carry) {
+  double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
+  if (hl == 0) up = carry;
   carry = 0.0;
 #pragma unroll
-  for (int j = NS - 1; j >= 1; --j) a[j] = (a[j] + a[j - 1]) * p[j];
-  a[0] = (a[0] + up) * p[0];
+  for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
+  sum[0] = x[0] + up;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) x[j] = sum[j] * p[j];
 }
 
 template <int NS>
 __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg, const Smem& S, int lane, int64_t b,
                                            int Tb, int Lb, float wgt) {
-  constexpr int Lpad = 32 * NS;
-  constexpr bool kRegTile = NS <= 2;  // tile-local alpha replay in registers
+  constexpr int Lpad = 16 * NS;
+  const int hl = lane & 15;
+  const bool isb = lane >= 16;  // beta half (phase 2 only)
   const int NT = (Tb + kTT - 1) / kTT;
   const int NBUF = cfg.NBUFP, NBUFG = cfg.NBUFG;
-  double* ck = (cfg.ckpt_global ? cfg.ws_ckpt + ((size_t)b * cfg.NTmax) * Lpad : S.ckpt) + lane;
+  double* ck = (cfg.ckpt_global ? cfg.ws_ckpt + ((size_t)b * cfg.NTmax) * Lpad : S.ckpt) + hl;
   int* cke = cfg.ckpt_global ? cfg.ws_cke + (size_t)b * cfg.NTmax : S.cke;
-  double a[NS];
+  double x[NS], sum[NS];
 #pragma unroll
-  for (int j = 0; j < NS; ++j) a[j] = 0.0;
+  for (int j = 0; j < NS; ++j) x[j] = 0.0;
   int Ea = 0;
-  double carry = 1.0;
-  // ------------------------------------------------------------------ phase 1: alpha
+  double carry = (lane == 0) ? 1.0 : 0.0;
+  // ------------------------------------------------------------------ phase 1: alpha (lanes 16-31 carry zeros)
   for (int k = 0; k < NT; ++k) {
     const int buf = k % NBUF;
     if (k > 0) {
-      Ea += rescale_pow2<NS>(a);
+      Ea += rescale_half<NS>(x);
+      if (!isb) {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) ck[(k * NS + j) * 32] = a[j];
-      if (lane == 0) cke[k] = Ea;
+        for (int j = 0; j < NS; ++j) ck[(k * NS + j) * 16] = x[j];
+        if (lane == 0) cke[k] = Ea;
+      }
     }
     mbar_wait(&S.pfull[buf], (k / NBUF) & 1);
-    const float* pt = S.ptile + buf * (kTT * Lpad) + lane * NS;
+    const float* pt = S.ptile + buf * (kTT * Lpad);
     const int nv = min(kTT, Tb - k * kTT);
-    if (nv == kTT) {
-#pragma unroll
-      for (int i = 0; i < kTT; ++i) {
-        double p[NS];
-        load_p<NS>(pt + i * Lpad, p);
-        alpha_step<NS>(a, p, lane, carry);
-      }
-    } else {
-      for (int i = 0; i < nv; ++i) {
-        double p[NS];
-        load_p<NS>(pt + i * Lpad, p);
-        alpha_step<NS>(a, p, lane, carry);
-      }
+#pragma unroll 2
+    for (int i = 0; i < nv; ++i) {
+      double p[NS];
+      load_p<NS>(pt + i * Lpad, hl, false, p);
+      chain_step<NS>(x, sum, p, hl, carry);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.pempty[buf]);
+    if (lane == 0) count_publish(&S.cnt[0], k + 1);
   }
   // ------------------------------------------------------------------ read-out (NoBlankCTC.py:58-68,:139)
   const int sl = Lb - 1;
   double mine = 0.0;
 #pragma unroll
   for (int j = 0; j < NS; ++j)
-    if (j == sl % NS) mine = a[j];
+    if (j == sl % NS) mine = x[j];
   const double zhat = __shfl_sync(0xffffffffu, mine, sl / NS);
-  const int Ez = Ea;
+  const int Ez = __shfl_sync(0xffffffffu, Ea, 0);
   if (lane == 0) P.loss[b] = (zhat > 0.0) ? (float)(-(log(zhat) + (double)Ez * 0.6931471805599453)) : INFINITY;
   if (P.grad == nullptr) return;
   const double zinv = (zhat > 0.0) ? (double)wgt / zhat : 0.0;  // sequence weight folded into gamma
-  // ------------------------------------------------------------------ phase 2: beta, gamma
-  // u(s) = beta_{t+1}(s) p_{t+1}(s).  Virtual start: u_{T_b}(L_b) = 1 makes beta_{T_b-1}(L_b-1) = 1 with no branch
-  // (state L_b itself has p = 0 and alpha = 0, so it contributes nothing).
-  double u[NS];
-#pragma unroll
-  for (int j = 0; j < NS; ++j) u[j] = (lane * NS + j == Lb) ? 1.0 : 0.0;
-  double bcarry = (Lb == Lpad) ? 1.0 : 0.0;
+  // ------------------------------------------------------------------ phase 2: beta (lanes 16-31) + alpha replay (0-15)
+  // beta half: position q of the half holds state Lpad-1-q; x = u_t(s) = beta_t(s) p_t(s).  Virtual start
+  // u_{T_b}(L_b) = 1 gives beta_{T_b-1}(L_b-1) = 1 without a branch (state L_b has p = 0 and alpha = 0).
   int Eb = 0;
+  if (isb) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) x[j] = (Lpad - 1 - (hl * NS + j) == Lb) ? 1.0 : 0.0;
+    carry = (hl == 0 && Lb == Lpad) ? 1.0 : 0.0;
+  }
+  double* at = S.abtile;               // [kTT][Lpad] alpha_t(s) (pre-scaled)
+  double* bt = S.abtile + kTT * Lpad;  // [kTT][Lpad] beta_t(s)
   for (int j2 = 0; j2 < NT; ++j2) {
     const int k = NT - 1 - j2;
     const int n = NT + j2;
     const int buf = n % NBUF;
     const int gbuf = j2 % NBUFG;
-    int EaK = 0;
-    if (k == 0) {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) a[j] = 0.0;
-      carry = 1.0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) a[j] = ck[(k * NS + j) * 32];
-      EaK = cke[k];
-    }
-    // gamma = alpha * beta * w / Z: the power-of-two part is split over both factors (range safety)
-    const int d = EaK + Eb - Ez;
+    // gamma = alpha * beta * w / Z; the power-of-two part is split over both factors (range safety)
+    const int EaK = (k == 0) ? 0 : cke[k];
+    const int Eb_all = __shfl_sync(0xffffffffu, Eb, 16);
+    const int d = EaK + Eb_all - Ez;
     const double s1 = pow2i(d / 2);
-    const double s2 = pow2i(d - d / 2) * zinv;
+    const double s2 = -(pow2i(d - d / 2) * zinv);  // negative: the row warps ADD gamma' = -w*gamma to the softmax row
+    if (!isb) {
+      if (k == 0) {
 #pragma unroll
-    for (int j = 0; j < NS; ++j) a[j] *= s1;  // exact; alpha replay runs pre-scaled
-    if (k == 0) carry = s1;
-    mbar_wait(&S.pfull[buf], (n / NBUF) & 1);
-    const float* pt = S.ptile + buf * (kTT * Lpad) + lane * NS;
-    const int nv = min(kTT, Tb - k * kTT);
-    double ar[kRegTile ? kTT : 1][NS];
-    double* at = S.atile + lane;
-    // replay alpha inside the tile
+        for (int j = 0; j < NS; ++j) x[j] = 0.0;
+        carry = (lane == 0) ? s1 : 0.0;
+      } else {
 #pragma unroll
-    for (int i = 0; i < kTT; ++i) {
-      if (i < nv) {
-        double p[NS];
-        load_p<NS>(pt + i * Lpad, p);
-        alpha_step<NS>(a, p, lane, carry);
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-          if constexpr (kRegTile) ar[i][j] = a[j];
-          else at[(i * NS + j) * 32] = a[j];
-        }
+        for (int j = 0; j < NS; ++j) x[j] = ck[(k * NS + j) * 16] * s1;  // exact: alpha replay runs pre-scaled
       }
+    }
+    mbar_wait(&S.pfull[buf], (n / NBUF) & 1);
+    const float* pt = S.ptile + buf * (kTT * Lpad);
+    const int nv = min(kTT, Tb - k * kTT);
+    // position -> state index of this lane's slots
+    const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
+    const int sdir = isb ? -1 : 1;
+    double* dst = (isb ? bt : at) + s0;
+#pragma unroll 2
+    for (int jj = 0; jj < nv; ++jj) {
+      const int i = isb ? (nv - 1 - jj) : jj;  // alpha walks up the tile, beta walks down
+      double p[NS];
+      load_p<NS>(pt + i * Lpad, hl, isb, p);
+      chain_step<NS>(x, sum, p, hl, carry);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) dst[i * Lpad + sdir * j] = isb ? sum[j] : x[j];
     }
     if (j2 >= NBUFG) mbar_wait(&S.gempty[gbuf], ((j2 / NBUFG) - 1) & 1);
-    float* gt = S.gtile + gbuf * (kTT * Lpad) + lane * NS;
-#pragma unroll
-    for (int ii = 0; ii < kTT; ++ii) {
-      const int i = kTT - 1 - ii;
-      if (i < nv) {
-        double p[NS], beta[NS];
-        load_p<NS>(pt + i * Lpad, p);
-        double dn = __shfl_down_sync(0xffffffffu, u[0], 1);
-        if (lane == 31) dn = bcarry;
-        bcarry = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS - 1; ++j) beta[j] = u[j] + u[j + 1];
-        beta[NS - 1] = u[NS - 1] + dn;
-        float g[NS];
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-          double al;
-          if constexpr (kRegTile) al = ar[i][j];
-          else al = at[(i * NS + j) * 32];
-          g[j] = (float)(al * (beta[j] * s2));
-          u[j] = beta[j] * p[j];
-        }
-        store_g<NS>(gt + i * Lpad, g);
-      }
+    __syncwarp();
+    float* gt = S.gtile + gbuf * (kTT * Lpad);
+    for (int idx = lane; idx < nv * Lpad; idx += 32) gt[idx] = (float)(at[idx] * (bt[idx] * s2));
+    {
+      // every lane takes part in the half-wide shuffles; only the beta half keeps the result
+      const int e = rescale_half<NS>(x);
+      if (isb) Eb += e;
     }
-    Eb += rescale_pow2<NS>(u);
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&S.gfull[gbuf]);
-      mbar_arrive(&S.pempty[buf]);
+      count_publish(&S.cnt[0], n + 1);
     }
   }
 }
 
 // ============================================================================ TMA producer warp
-// One elected lane walks the sequence's rows tile by tile -- phase 1 upwards, phase 2 downwards (most recently
-// read rows first, so the re-read hits L2) -- and issues one bulk copy per row (the 16-byte aligned superset
-// of the 4-byte aligned row) into the shared-memory ring.  Phase-1 copies carry an L2 evict_last policy, phase-2
-// copies evict_first.
 __device__ __forceinline__ void producer_warp(const Problem& P, const FusedCfg& cfg, const Smem& S, int lane, int64_t b,
                                               int Tb) {
   if (lane != 0) return;
   const int NT = (Tb + kTT - 1) / kTT;
   const int total = (P.grad != nullptr) ? 2 * NT : NT;
-  const int C = (int)P.C;
+  const uint32_t C4 = (uint32_t)P.C * 4u;
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-  const uintptr_t safe_end = (reinterpret_cast<uintptr_t>(cfg.logits_end) + 15) & ~uintptr_t(15);
-  const bool end_unaligned = (reinterpret_cast<uintptr_t>(cfg.logits_end) & 15) != 0;
+  const uint64_t stride = (uint64_t)P.B * C4;  // bytes between rows t and t+1 of one sequence
+  const uint64_t seq0 = reinterpret_cast<uint64_t>(P.logits) + (uint64_t)b * C4;
+  const uint64_t end = reinterpret_cast<uint64_t>(cfg.logits_end);
+  const bool guard_last = (end & 15) != 0 && b == P.B - 1 && Tb == P.T;  // only the tensor's last row can over-read
+  const uint32_t ring0 = smem_u32(S.ring);
+  const uint32_t slot_bytes = (uint32_t)kTT * cfg.RS;
+  int slot = 0, use = 0;
   for (int n = 0; n < total; ++n) {
     const int k = n < NT ? n : 2 * NT - 1 - n;
-    const int slot = n % cfg.NSLOT;
-    const int use = n / cfg.NSLOT;
     if (use >= 1) mbar_wait(&S.sempty[slot], (use - 1) & 1);
     const int nv = min(kTT, Tb - k * kTT);
-    unsigned char* dst = S.ring + (size_t)slot * kTT * cfg.RS;
-    const float* row0 = P.logits + ((int64_t)k * kTT * P.B + b) * C;
-    const int64_t strideT = P.B * (int64_t)C;
+    const uint32_t bar = smem_u32(&S.sfull[slot]);
+    const uint64_t pol = n < NT ? pol_keep : pol_stream;
+    uint32_t dst = ring0 + slot * slot_bytes;
+    uint64_t a = seq0 + (uint64_t)k * kTT * stride;
     uint32_t bytes = 0;
-    for (int i = 0; i < nv; ++i) {
-      const uintptr_t a = reinterpret_cast<uintptr_t>(row0 + i * strideT);
-      const uintptr_t a0 = a & ~uintptr_t(15);
-      const uint32_t nb = (uint32_t)(((a + (uintptr_t)C * 4 + 15) & ~uintptr_t(15)) - a0);
-      // the very last row of an unaligned tensor would be over-read by < 16 bytes: copy it by hand instead
-      if (end_unaligned && a0 + nb == safe_end) {
+    for (int i = 0; i < nv; ++i, a += stride, dst += cfg.RS) {
+      const uint32_t nb = (((uint32_t)a & 15u) + C4 + 15u) & ~15u;
+      if (guard_last && k * kTT + i == P.T - 1) {
+        // the very last row of an unaligned tensor would be over-read by < 16 bytes: copy it by hand
         const float* src = reinterpret_cast<const float*>(a);
-        float* d = reinterpret_cast<float*>(dst + (size_t)i * cfg.RS) + ((a >> 2) & 3);
-        for (int c = 0; c < C; ++c) d[c] = __ldg(src + c);
+        float* d = reinterpret_cast<float*>(S.ring + (size_t)slot * slot_bytes + (size_t)i * cfg.RS) + ((a >> 2) & 3);
+        for (uint32_t c = 0; c < (uint32_t)P.C; ++c) d[c] = __ldg(src + c);
       } else {
+        bulk_g2s(dst, a & ~uint64_t(15), nb, bar, pol);
         bytes += nb;
       }
     }
+    // the phase cannot complete before this arrival, so expecting the bytes after issuing the copies is safe
     mbar_arrive_expect_tx(&S.sfull[slot], bytes);
-    const uint64_t pol = n < NT ? pol_keep : pol_stream;
-    for (int i = 0; i < nv; ++i) {
-      const uintptr_t a = reinterpret_cast<uintptr_t>(row0 + i * strideT);
-      const uintptr_t a0 = a & ~uintptr_t(15);
-      const uint32_t nb = (uint32_t)(((a + (uintptr_t)C * 4 + 15) & ~uintptr_t(15)) - a0);
-      if (!(end_unaligned && a0 + nb == safe_end))
-        bulk_g2s(dst + (size_t)i * cfg.RS, reinterpret_cast<const void*>(a0), nb, &S.sfull[slot], pol);
-    }
+    count_publish(&S.cnt[1], n + 1);
+    if (++slot == cfg.NSLOT) { slot = 0; ++use; }
   }
 }
 
 // ============================================================================ row warps
-// Geometry of one (t,b) row seen as 16-byte chunks: the row starts `off4` floats into chunk 0 and
-// ends `rem` floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0).  `srow` is the row's
-// copy in the shared-memory ring (same 16-byte phase as in global memory).
+// Geometry of one (t,b) row seen as 16-byte chunks: the row starts `off4` floats into chunk 0 and ends `rem`
+// floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0).  `srow` is the row's copy in the
+// shared-memory ring (same 16-byte phase as in global memory).
 struct RowGeom {
-  const float4* srow;
+  float4* srow;
   int64_t goff;        // element offset of the row in logits / grad
   int off4, nch, rem;  // rem in 1..4 = valid floats in the last chunk
 };
@@ -398,8 +399,9 @@ template <int NS, int LPR, int CPL>
 struct Rows {
   static constexpr int R = 32 / LPR;      // rows per warp pass
   static constexpr int NP = kTT / R;      // passes per tile
-  static constexpr int Lpad = 32 * NS;
-  static constexpr int NSL = Lpad / LPR;  // states per lane in the emission gather
+  static constexpr int Lpad = 16 * NS;
+  static constexpr int NSL = Lpad / LPR;  // states per lane in the emission gather / gamma scatter
+  static constexpr bool kLabRegs = NSL <= 8;
   static constexpr int SEG = LPR * CPL;   // chunks per row segment
   static_assert(R <= kTT && NP * R == kTT, "tile must be a whole number of passes");
 
@@ -413,21 +415,35 @@ struct Rows {
   const uint64_t pol_stream;
   const float wgt;
   const uintptr_t base_addr;
+  int labr[kLabRegs ? NSL : 1];  // this lane's labels (-1 = no state)
 
   __device__ __forceinline__ Rows(const Problem& P_, const FusedCfg& cfg_, const Smem& S_, int lane_, int wrow_,
                                   int64_t b_, int Tb_, int Lb_, float wgt_)
       : P(P_), cfg(cfg_), S(S_), lane(lane_), li(lane_ & (LPR - 1)), gi(lane_ / LPR), wrow(wrow_), b(b_), Tb(Tb_),
         Lb(Lb_), C((int)P_.C), lse_arr(cfg_.lse_global ? cfg_.ws_lse + (size_t)b_ * P_.T : S_.lse),
-        pol_stream(policy_evict_first()), wgt(wgt_), base_addr(reinterpret_cast<uintptr_t>(P_.logits)) {}
+        pol_stream(policy_evict_first()), wgt(wgt_), base_addr(reinterpret_cast<uintptr_t>(P_.logits)) {
+    if constexpr (kLabRegs) {
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) {
+        const int st = li + j * LPR;
+        labr[j] = st < Lb_ ? S_.lab[st] : -1;
+      }
+    }
+  }
+  __device__ __forceinline__ int label(int j) const {
+    if constexpr (kLabRegs) return labr[j];
+    const int st = li + j * LPR;
+    return st < Lb ? S.lab[st] : -1;
+  }
 
   // row t of this sequence; `slot_rows` = start of the ring slot holding the tile, i = row inside the tile
-  __device__ __forceinline__ RowGeom geom(int t, const unsigned char* slot_rows, int i) const {
+  __device__ __forceinline__ RowGeom geom(int t, unsigned char* slot_rows, int i) const {
     RowGeom g;
     g.goff = ((int64_t)t * P.B + b) * C;
     g.off4 = (int)(((base_addr >> 2) + (uintptr_t)g.goff) & 3);
     g.nch = (g.off4 + C + 3) >> 2;
     g.rem = g.off4 + C - 4 * (g.nch - 1);
-    g.srow = reinterpret_cast<const float4*>(slot_rows + (size_t)i * cfg.RS);
+    g.srow = reinterpret_cast<float4*>(slot_rows + (size_t)i * cfg.RS);
     return g;
   }
 
@@ -489,19 +505,23 @@ struct Rows {
     if (act) {
       const float* xr = reinterpret_cast<const float*>(g.srow) + g.off4;
       const float lb2 = lse * kLog2e;
+      float xv[NSL];
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
-        const int st = li + j * LPR;
-        float pv = 0.f;
-        if (st < Lb) pv = fmaxf(ex2f(fmaf(xr[S.lab[st]], kLog2e, -lb2)), kPMin);
-        ptile_buf[i * Lpad + st] = pv;
+        const int l = label(j);
+        xv[j] = xr[l >= 0 ? l : 0];
+      }
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) {
+        const float pv = label(j) >= 0 ? fmaxf(ex2f(fmaf(xv[j], kLog2e, -lb2)), kPMin) : 0.f;
+        ptile_buf[i * Lpad + li + j * LPR] = pv;
       }
     }
   }
 
   // ---------------------------------------------------------------- phase 1: one tile
-  __device__ __forceinline__ void forward_tile(int k, int nv, const unsigned char* slot_rows, float* ptile_buf) const {
-#pragma unroll
+  __device__ __forceinline__ void forward_tile(int k, int nv, unsigned char* slot_rows, float* ptile_buf) const {
+#pragma unroll 1
     for (int pr = 0; pr < NP; ++pr) {
       const int i = pr * R + gi;
       const bool act = i < nv;
@@ -529,8 +549,8 @@ struct Rows {
   }
 
   // ---------------------------------------------------------------- phase 2 stage A: emissions again
-  __device__ __forceinline__ void emit_tile(int k, int nv, const unsigned char* slot_rows, float* ptile_buf) const {
-#pragma unroll
+  __device__ __forceinline__ void emit_tile(int k, int nv, unsigned char* slot_rows, float* ptile_buf) const {
+#pragma unroll 1
     for (int pr = 0; pr < NP; ++pr) {
       const int i = pr * R + gi;
       const bool act = i < nv;
@@ -540,15 +560,18 @@ struct Rows {
   }
 
   // ---------------------------------------------------------------- gradient row pieces
+  // chunks of one row segment -> global; only chunk 0 and chunk nch-1 can be partial
+  template <bool kSingle>
   __device__ __forceinline__ void store_seg(float* grow, const RowGeom& g, int seg, const float4 (&v)[CPL]) const {
     float4* dst = reinterpret_cast<float4*>(grow - g.off4) + seg * SEG + li;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int q = seg * SEG + li + c * LPR;
       if (q < g.nch) {
+        const bool may_partial = !kSingle || c == 0 || c + 2 >= CPL;
         const bool head = (q == 0) && g.off4 != 0;
         const bool tail = (q == g.nch - 1) && g.rem != 4;
-        if (!head && !tail) {
+        if (!may_partial || (!head && !tail)) {
           stg_f4_hint(dst + c * LPR, v[c], pol_stream);
         } else {
           float* e = reinterpret_cast<float*>(dst + c * LPR);
@@ -562,63 +585,65 @@ struct Rows {
       }
     }
   }
-  __device__ __forceinline__ void grad_seg(const float4* d4, const RowGeom& g, int seg, float lb2, float4 (&v)[CPL]) const {
-    const float4* src = g.srow + seg * SEG + li;
+  // in place in the row's shared-memory copy: x -> w * softmax(x)
+  __device__ __forceinline__ void softmax_seg(const RowGeom& g, int seg, float lb2) const {
+    float4* src = g.srow + seg * SEG + li;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int q = seg * SEG + li + c * LPR;
       if (q < g.nch) {
-        const float4 x = src[c * LPR];
-        const float4 d = d4[q];
-        v[c].x = fmaf(ex2f(fmaf(x.x, kLog2e, -lb2)), wgt, -d.x);
-        v[c].y = fmaf(ex2f(fmaf(x.y, kLog2e, -lb2)), wgt, -d.y);
-        v[c].z = fmaf(ex2f(fmaf(x.z, kLog2e, -lb2)), wgt, -d.z);
-        v[c].w = fmaf(ex2f(fmaf(x.w, kLog2e, -lb2)), wgt, -d.w);
+        float4 x = src[c * LPR];
+        x.x = wgt * ex2f(fmaf(x.x, kLog2e, -lb2));
+        x.y = wgt * ex2f(fmaf(x.y, kLog2e, -lb2));
+        x.z = wgt * ex2f(fmaf(x.z, kLog2e, -lb2));
+        x.w = wgt * ex2f(fmaf(x.w, kLog2e, -lb2));
+        src[c * LPR] = x;
       }
     }
   }
-  __device__ __forceinline__ void scatter_add(float* dl, const RowGeom& g, bool act, int i, const float* gtile_buf) const {
-    if (act) {
+  template <bool kSingle>
+  __device__ __forceinline__ void copy_out_seg(float* grow, const RowGeom& g, int seg) const {
+    const float4* src = g.srow + seg * SEG + li;
+    float4 v[CPL];
 #pragma unroll
-      for (int j = 0; j < NSL; ++j) {
-        const int st = li + j * LPR;
-        if (st < Lb) atomicAdd(&dl[S.lab[st] + g.off4], gtile_buf[i * Lpad + st]);
-      }
+    for (int c = 0; c < CPL; ++c) {
+      const int q = seg * SEG + li + c * LPR;
+      if (q < g.nch) v[c] = src[c * LPR];
     }
-  }
-  __device__ __forceinline__ void scatter_clear(float* dl, const RowGeom& g, bool act) const {
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < NSL; ++j) {
-        const int st = li + j * LPR;
-        if (st < Lb) dl[S.lab[st] + g.off4] = 0.f;
-      }
-    }
+    store_seg<kSingle>(grow, g, seg, v);
   }
 
   // ---------------------------------------------------------------- phase 2 stage B: one tile
-  __device__ __forceinline__ void backward_tile(int k, int nv, const unsigned char* slot_rows, const float* gtile_buf) const {
-    float* dl = S.delta + (wrow * R + gi) * cfg.Cd;
-    const float4* d4 = reinterpret_cast<const float4*>(dl);
-#pragma unroll
+  // w*softmax is formed in place in the row's shared-memory copy, -w*gamma is scattered onto it with shared-memory
+  // atomics (repeated labels accumulate), then the row streams out with 128-bit stores.
+  __device__ __forceinline__ void backward_tile(int k, int nv, unsigned char* slot_rows, const float* gtile_buf) const {
+#pragma unroll 1
     for (int pr = 0; pr < NP; ++pr) {
       const int i = pr * R + gi;
       const bool act = i < nv;
       const RowGeom g = geom(k * kTT + i, slot_rows, i);
-      scatter_add(dl, g, act, i, gtile_buf);
-      __syncwarp();
       if (act) {
         const float lb2 = lse_arr[k * kTT + i] * kLog2e;
-        float* grow = P.grad + g.goff;
-        for (int seg = 0; seg < cfg.NSEG; ++seg) {
-          float4 v[CPL];
-          grad_seg(d4, g, seg, lb2, v);
-          store_seg(grow, g, seg, v);
+        for (int seg = 0; seg < cfg.NSEG; ++seg) softmax_seg(g, seg, lb2);
+      }
+      __syncwarp();
+      if (act) {
+        float* xr = reinterpret_cast<float*>(g.srow) + g.off4;
+#pragma unroll
+        for (int j = 0; j < NSL; ++j) {
+          const int l = label(j);
+          if (l >= 0) atomicAdd(&xr[l], gtile_buf[i * Lpad + li + j * LPR]);
         }
       }
       __syncwarp();
-      scatter_clear(dl, g, act);
-      __syncwarp();
+      if (act) {
+        float* grow = P.grad + g.goff;
+        if (cfg.NSEG == 1) {
+          copy_out_seg<true>(grow, g, 0);
+        } else {
+          for (int seg = 0; seg < cfg.NSEG; ++seg) copy_out_seg<false>(grow, g, seg);
+        }
+      }
     }
   }
 
@@ -629,7 +654,7 @@ struct Rows {
     for (int c = 0; c < CPL; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t t = (int64_t)t_begin + wrow * R + gi; t < P.T; t += kNW * R) {
       const RowGeom g = geom((int)t, nullptr, 0);
-      for (int seg = 0; seg < cfg.NSEG; ++seg) store_seg(P.grad + g.goff, g, seg, z);
+      for (int seg = 0; seg < cfg.NSEG; ++seg) store_seg<false>(P.grad + g.goff, g, seg, z);
     }
   }
 
@@ -641,7 +666,8 @@ struct Rows {
     for (int k = wrow; k < NT; k += kNW) {
       const int buf = k % NBUF;
       const int slot = k % NSLOT;
-      if (k >= NBUF) mbar_wait(&S.pempty[buf], ((k / NBUF) - 1) & 1);
+      if (k >= NBUF) count_wait(&S.cnt[0], k - NBUF + 1);  // chain is done with the p-tile buffer's previous use
+      count_wait(&S.cnt[1], k + 1);                         // the copy has been issued => the parity wait is sound
       mbar_wait(&S.sfull[slot], (k / NSLOT) & 1);
       forward_tile(k, min(kTT, Tb - k * kTT), S.ring + slot * slot_bytes, S.ptile + buf * (kTT * Lpad));
       __syncwarp();
@@ -660,14 +686,16 @@ struct Rows {
       const int n = NT + j2;
       const int buf = n % NBUF, gbuf = j2 % NBUFG, slot = n % NSLOT;
       const int nv = min(kTT, Tb - k * kTT);
-      const unsigned char* rows = S.ring + slot * slot_bytes;
-      if (n >= NBUF) mbar_wait(&S.pempty[buf], ((n / NBUF) - 1) & 1);
+      unsigned char* rows = S.ring + slot * slot_bytes;
+      if (n >= NBUF) count_wait(&S.cnt[0], n - NBUF + 1);
+      count_wait(&S.cnt[1], n + 1);
       mbar_wait(&S.sfull[slot], (n / NSLOT) & 1);
       emit_tile(k, nv, rows, S.ptile + buf * (kTT * Lpad));
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.pfull[buf]);
       mbar_wait(&S.gfull[gbuf], (j2 / NBUFG) & 1);
       backward_tile(k, nv, rows, S.gtile + gbuf * (kTT * Lpad));
+      __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S.gempty[gbuf]);
         mbar_arrive(&S.sempty[slot]);
@@ -678,23 +706,22 @@ struct Rows {
 
 // ============================================================================ kernel
 template <int NS, int LPR, int CPL>
-__global__ void __launch_bounds__(kThreads, 3) nbctc_fused_kernel(const Problem P, const FusedCfg cfg) {
+__global__ void __launch_bounds__(kThreads, (NS <= 4 ? 4 : 2)) nbctc_fused_kernel(const Problem P, const FusedCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem S;
   S.pfull = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar);
-  S.pempty = S.pfull + kMaxBuf;
-  S.gfull = S.pempty + kMaxBuf;
+  S.gfull = S.pfull + kMaxBuf;
   S.gempty = S.gfull + kMaxBuf;
   S.sfull = S.gempty + kMaxBuf;
   S.sempty = S.sfull + kMaxSlot;
+  S.cnt = reinterpret_cast<volatile int*>(S.sempty + kMaxSlot);
   S.lab = reinterpret_cast<int*>(smem_raw + cfg.o_lab);
   S.lse = reinterpret_cast<float*>(smem_raw + cfg.o_lse);
   S.ckpt = reinterpret_cast<double*>(smem_raw + cfg.o_ckpt);
   S.cke = reinterpret_cast<int*>(smem_raw + cfg.o_cke);
   S.ptile = reinterpret_cast<float*>(smem_raw + cfg.o_ptile);
   S.gtile = reinterpret_cast<float*>(smem_raw + cfg.o_gtile);
-  S.atile = reinterpret_cast<double*>(smem_raw + cfg.o_atile);
-  S.delta = reinterpret_cast<float*>(smem_raw + cfg.o_delta);
+  S.abtile = reinterpret_cast<double*>(smem_raw + cfg.o_abtile);
   S.ring = smem_raw + cfg.o_ring;
 
   const int64_t b = blockIdx.x;
@@ -704,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 3) nbctc_fused_kernel(const Problem 
   const int Tb = (int)Tb64, Lb = (int)Lb64;
   int bad = 0;
   if (ok) {
-    for (int s = tid; s < 32 * NS; s += blockDim.x) {
+    for (int s = tid; s < 16 * NS; s += blockDim.x) {
       int l = 0;
       if (s < Lb) {
         l = P.labels[b * P.Lmax + s];
@@ -715,7 +742,6 @@ __global__ void __launch_bounds__(kThreads, 3) nbctc_fused_kernel(const Problem 
   }
   if (tid < kMaxBuf) {
     mbar_init(&S.pfull[tid], 1);
-    mbar_init(&S.pempty[tid], 1);
     mbar_init(&S.gfull[tid], 1);
     mbar_init(&S.gempty[tid], 1);
   }
@@ -723,10 +749,8 @@ __global__ void __launch_bounds__(kThreads, 3) nbctc_fused_kernel(const Problem 
     mbar_init(&S.sfull[tid], 1);
     mbar_init(&S.sempty[tid], 1);
   }
-  {
-    const int nd = kNW * (32 / LPR) * cfg.Cd;
-    for (int i = tid; i < nd; i += blockDim.x) S.delta[i] = 0.f;
-  }
+  if (tid < 2) S.cnt[tid] = 0;
+  static_assert(kNW == 4, "the gamma-tile ring depth must equal the number of row warps (same waiter per buffer)");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   bad = __syncthreads_or(bad);

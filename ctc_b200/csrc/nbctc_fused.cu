@@ -33,8 +33,8 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax, const void* logits
   pl.ok = false;
   if (Lmax > 256 || T > ((int64_t)1 << 28) || C > ((int64_t)1 << 22)) return pl;
   FusedCfg& c = pl.cfg;
-  c.NS = Lmax <= 32 ? 1 : Lmax <= 64 ? 2 : Lmax <= 128 ? 4 : 8;
-  c.Lpad = 32 * c.NS;
+  c.NS = Lmax <= 32 ? 2 : Lmax <= 64 ? 4 : Lmax <= 128 ? 8 : 16;  // 16 chain lanes per direction
+  c.Lpad = 16 * c.NS;
   // chunks per row: rows of a tensor with C % 4 == 0 all share the base pointer's alignment
   const int off_base = (int)((reinterpret_cast<uintptr_t>(logits_ptr) >> 2) & 3);
   const int64_t nch = (C % 4 == 0) ? (off_base + C + 3) / 4 : (3 + C + 3) / 4;
@@ -54,34 +54,34 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax, const void* logits
   c.RS = (int)(16 * nch);
   c.logits_end = nullptr;
   c.NTmax = (int)((T + kTT - 1) / kTT);
-  c.Cd = (int)((C + 3 + 3) / 4 * 4 + 4);
   const size_t budget = 200 * 1024;
   auto layout = [&](int nslot, bool ck_glob, bool lse_glob) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
-    c.NSLOT = nslot; c.NBUFP = 2 * kNW; c.NBUFG = kNW; c.ckpt_global = ck_glob; c.lse_global = lse_glob;
+    c.NSLOT = nslot; c.NBUFP = c.Lpad <= 64 ? 2 * kNW : kNW + 1; c.NBUFG = kNW; c.ckpt_global = ck_glob;
+    c.lse_global = lse_glob;
     const int nbuf = c.NBUFP;
-    c.o_bar = take(sizeof(uint64_t) * (4 * kMaxBuf + 2 * kMaxSlot));
+    c.o_bar = take(sizeof(uint64_t) * (3 * kMaxBuf + 2 * kMaxSlot) + 16);
     c.o_lab = take(sizeof(int) * c.Lpad);
     c.o_lse = take(lse_glob ? 16 : sizeof(float) * T);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)c.NTmax * c.Lpad);
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)c.NTmax);
     c.o_ptile = take(sizeof(float) * (size_t)nbuf * kTT * c.Lpad);
     c.o_gtile = take(sizeof(float) * (size_t)c.NBUFG * kTT * c.Lpad);
-    c.o_atile = take(c.NS <= 2 ? 16 : sizeof(double) * (size_t)kTT * c.Lpad);
-    c.o_delta = take(sizeof(float) * (size_t)kNW * (32 / c.LPR) * c.Cd);
+    c.o_abtile = take(sizeof(double) * 2 * (size_t)kTT * c.Lpad);
     off = align_up(off, 128);
     c.o_ring = take((size_t)nslot * kTT * c.RS);
     c.smem_bytes = (uint32_t)off;
     return off;
   };
-  // pass 0: everything in shared memory and <= 74 KB so that 3 CTAs share an SM; later passes move the
-  // checkpoints / row constants to the workspace and let one CTA take up to ~200 KB.
+  // pass 0: everything in shared memory and <= 55 KB so that 4 CTAs share an SM; pass 1: <= 74 KB (3 CTAs);
+  // later passes move the checkpoints / row constants to the workspace and let one CTA take up to ~200 KB.
   bool placed = false;
-  for (int pass = 0; pass < 3 && !placed; ++pass) {
-    const bool ckg = pass >= 1, lsg = pass >= 2;
-    const size_t cap = (pass == 0) ? 74 * 1024 : budget;
-    for (int nslot = (pass == 0 ? 7 : 6); nslot >= 3 && !placed; --nslot)
+  for (int pass = 0; pass < 4 && !placed; ++pass) {
+    const bool ckg = pass >= 2, lsg = pass >= 3;
+    const size_t cap = pass == 0 ? 55 * 1024 : pass == 1 ? 74 * 1024 : budget;
+    const int lo = pass <= 1 ? 5 : 3;
+    for (int nslot = 7; nslot >= lo && !placed; --nslot)
       if (layout(nslot, ckg, lsg) <= cap) placed = true;
   }
   if (!placed) return pl;
@@ -142,10 +142,10 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
   if (pl.cfg.lse_global) pl.cfg.ws_lse = reinterpret_cast<float*>(w + off);
   pl.cfg.logits_end = p.logits + p.T * p.B * p.C;
   switch (pl.cfg.NS) {
-    case 1: return launch_fused_ns1(p, pl.cfg, stream);
     case 2: return launch_fused_ns2(p, pl.cfg, stream);
     case 4: return launch_fused_ns4(p, pl.cfg, stream);
-    default: return launch_fused_ns8(p, pl.cfg, stream);
+    case 8: return launch_fused_ns8(p, pl.cfg, stream);
+    default: return launch_fused_ns16(p, pl.cfg, stream);
   }
 }
 
