@@ -152,6 +152,23 @@ __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the
   return __hiloint2double((1023 + e) << 20, 0);
 }
 
+// Optional role profiler (compile with -DNBCTC_PROF): per-warp cycle counters split into wait / work buckets,
+// dumped to a debug buffer.  Compiled out of the product build.
+#ifdef NBCTC_PROF
+extern __device__ long long* g_nbctc_prof;
+#define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0_ = clock64();
+#define PROF_SCOPE(i, stmt) { const long long t_ = clock64(); stmt; prof_[i] += clock64() - t_; }
+#define PROF_DUMP(warp_)                                                                          \
+  if (lane == 0 && g_nbctc_prof != nullptr) {                                                     \
+    prof_[7] = clock64() - prof_t0_;                                                              \
+    for (int i_ = 0; i_ < 8; ++i_) g_nbctc_prof[((size_t)b * 6 + (warp_)) * 8 + i_] = prof_[i_];  \
+  }
+#else
+#define PROF_DECL
+#define PROF_SCOPE(i, stmt) { stmt; }
+#define PROF_DUMP(warp_)
+#endif
+
 struct Smem {
   uint64_t *pfull, *gfull, *gempty, *sfull, *sempty;
   volatile int* cnt;  // [0] p-tiles consumed by the chain, [1] row tiles issued by the producer (monotonic)
@@ -233,6 +250,7 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
   for (int j = 0; j < NS; ++j) x[j] = 0.0;
   int Ea = 0;
   double carry = (lane == 0) ? 1.0 : 0.0;
+  PROF_DECL
   // ------------------------------------------------------------------ phase 1: alpha (lanes 16-31 carry zeros)
   for (int k = 0; k < NT; ++k) {
     const int buf = k % NBUF;
@@ -244,15 +262,16 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
         if (lane == 0) cke[k] = Ea;
       }
     }
-    mbar_wait(&S.pfull[buf], (k / NBUF) & 1);
+    PROF_SCOPE(0, mbar_wait(&S.pfull[buf], (k / NBUF) & 1))
     const float* pt = S.ptile + buf * (kTT * Lpad);
     const int nv = min(kTT, Tb - k * kTT);
+    PROF_SCOPE(1,
 #pragma unroll 2
     for (int i = 0; i < nv; ++i) {
       double p[NS];
       load_p<NS>(pt + i * Lpad, hl, false, p);
       chain_step<NS>(x, sum, p, hl, carry);
-    }
+    })
     __syncwarp();
     if (lane == 0) count_publish(&S.cnt[0], k + 1);
   }
@@ -265,7 +284,10 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
   const double zhat = __shfl_sync(0xffffffffu, mine, sl / NS);
   const int Ez = __shfl_sync(0xffffffffu, Ea, 0);
   if (lane == 0) P.loss[b] = (zhat > 0.0) ? (float)(-(log(zhat) + (double)Ez * 0.6931471805599453)) : INFINITY;
-  if (P.grad == nullptr) return;
+  if (P.grad == nullptr) {
+    PROF_DUMP(0)
+    return;
+  }
   const double zinv = (zhat > 0.0) ? (double)wgt / zhat : 0.0;  // sequence weight folded into gamma
   // ------------------------------------------------------------------ phase 2: beta (lanes 16-31) + alpha replay (0-15)
   // beta half: position q of the half holds state Lpad-1-q; x = u_t(s) = beta_t(s) p_t(s).  Virtual start
@@ -299,13 +321,14 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
         for (int j = 0; j < NS; ++j) x[j] = ck[(k * NS + j) * 16] * s1;  // exact: alpha replay runs pre-scaled
       }
     }
-    mbar_wait(&S.pfull[buf], (n / NBUF) & 1);
+    PROF_SCOPE(2, mbar_wait(&S.pfull[buf], (n / NBUF) & 1))
     const float* pt = S.ptile + buf * (kTT * Lpad);
     const int nv = min(kTT, Tb - k * kTT);
     // position -> state index of this lane's slots
     const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
     const int sdir = isb ? -1 : 1;
     double* dst = (isb ? bt : at) + s0;
+    PROF_SCOPE(3,
 #pragma unroll 2
     for (int jj = 0; jj < nv; ++jj) {
       const int i = isb ? (nv - 1 - jj) : jj;  // alpha walks up the tile, beta walks down
@@ -314,11 +337,11 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
       chain_step<NS>(x, sum, p, hl, carry);
 #pragma unroll
       for (int j = 0; j < NS; ++j) dst[i * Lpad + sdir * j] = isb ? sum[j] : x[j];
-    }
-    if (j2 >= NBUFG) mbar_wait(&S.gempty[gbuf], ((j2 / NBUFG) - 1) & 1);
+    })
+    if (j2 >= NBUFG) PROF_SCOPE(4, mbar_wait(&S.gempty[gbuf], ((j2 / NBUFG) - 1) & 1))
     __syncwarp();
     float* gt = S.gtile + gbuf * (kTT * Lpad);
-    for (int idx = lane; idx < nv * Lpad; idx += 32) gt[idx] = (float)(at[idx] * (bt[idx] * s2));
+    PROF_SCOPE(5, for (int idx = lane; idx < nv * Lpad; idx += 32) gt[idx] = (float)(at[idx] * (bt[idx] * s2));)
     {
       // every lane takes part in the half-wide shuffles; only the beta half keeps the result
       const int e = rescale_half<NS>(x);
@@ -330,6 +353,7 @@ __device__ __forceinline__ void chain_warp(const Problem& P, const FusedCfg& cfg
       count_publish(&S.cnt[0], n + 1);
     }
   }
+  PROF_DUMP(0)
 }
 
 // ============================================================================ TMA producer warp
@@ -347,9 +371,10 @@ __device__ __forceinline__ void producer_warp(const Problem& P, const FusedCfg& 
   const uint32_t ring0 = smem_u32(S.ring);
   const uint32_t slot_bytes = (uint32_t)kTT * cfg.RS;
   int slot = 0, use = 0;
+  PROF_DECL
   for (int n = 0; n < total; ++n) {
     const int k = n < NT ? n : 2 * NT - 1 - n;
-    if (use >= 1) mbar_wait(&S.sempty[slot], (use - 1) & 1);
+    if (use >= 1) PROF_SCOPE(n < NT ? 0 : 1, mbar_wait(&S.sempty[slot], (use - 1) & 1))
     const int nv = min(kTT, Tb - k * kTT);
     const uint32_t bar = smem_u32(&S.sfull[slot]);
     const uint64_t pol = n < NT ? pol_keep : pol_stream;
@@ -373,6 +398,7 @@ __device__ __forceinline__ void producer_warp(const Problem& P, const FusedCfg& 
     count_publish(&S.cnt[1], n + 1);
     if (++slot == cfg.NSLOT) { slot = 0; ++use; }
   }
+  PROF_DUMP(5)
 }
 
 // ============================================================================ row warps
@@ -662,21 +688,26 @@ struct Rows {
     const int NT = (Tb + kTT - 1) / kTT;
     const int NBUF = cfg.NBUFP, NBUFG = cfg.NBUFG, NSLOT = cfg.NSLOT;
     const size_t slot_bytes = (size_t)kTT * cfg.RS;
+    PROF_DECL
     // ---- phase 1: tiles k = wrow, wrow+NW, ...
     for (int k = wrow; k < NT; k += kNW) {
       const int buf = k % NBUF;
       const int slot = k % NSLOT;
+      PROF_SCOPE(0,
       if (k >= NBUF) count_wait(&S.cnt[0], k - NBUF + 1);  // chain is done with the p-tile buffer's previous use
       count_wait(&S.cnt[1], k + 1);                         // the copy has been issued => the parity wait is sound
-      mbar_wait(&S.sfull[slot], (k / NSLOT) & 1);
-      forward_tile(k, min(kTT, Tb - k * kTT), S.ring + slot * slot_bytes, S.ptile + buf * (kTT * Lpad));
+      mbar_wait(&S.sfull[slot], (k / NSLOT) & 1);)
+      PROF_SCOPE(1, forward_tile(k, min(kTT, Tb - k * kTT), S.ring + slot * slot_bytes, S.ptile + buf * (kTT * Lpad));)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S.pfull[buf]);
         mbar_arrive(&S.sempty[slot]);
       }
     }
-    if (P.grad == nullptr) return;
+    if (P.grad == nullptr) {
+      PROF_DUMP(1 + wrow)
+      return;
+    }
     if (Tb < P.T) zero_rows(Tb);
     // ---- phase 2: the same warp owns the same tiles (it wrote their lse values), walked downwards:
     // A(k) = emissions -> chain, B(k) = gradient rows once the chain has produced gamma(k).
@@ -687,20 +718,22 @@ struct Rows {
       const int buf = n % NBUF, gbuf = j2 % NBUFG, slot = n % NSLOT;
       const int nv = min(kTT, Tb - k * kTT);
       unsigned char* rows = S.ring + slot * slot_bytes;
+      PROF_SCOPE(2,
       if (n >= NBUF) count_wait(&S.cnt[0], n - NBUF + 1);
       count_wait(&S.cnt[1], n + 1);
-      mbar_wait(&S.sfull[slot], (n / NSLOT) & 1);
-      emit_tile(k, nv, rows, S.ptile + buf * (kTT * Lpad));
+      mbar_wait(&S.sfull[slot], (n / NSLOT) & 1);)
+      PROF_SCOPE(3, emit_tile(k, nv, rows, S.ptile + buf * (kTT * Lpad));)
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.pfull[buf]);
-      mbar_wait(&S.gfull[gbuf], (j2 / NBUFG) & 1);
-      backward_tile(k, nv, rows, S.gtile + gbuf * (kTT * Lpad));
+      PROF_SCOPE(4, mbar_wait(&S.gfull[gbuf], (j2 / NBUFG) & 1))
+      PROF_SCOPE(5, backward_tile(k, nv, rows, S.gtile + gbuf * (kTT * Lpad));)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S.gempty[gbuf]);
         mbar_arrive(&S.sempty[slot]);
       }
     }
+    PROF_DUMP(1 + wrow)
   }
 };
 

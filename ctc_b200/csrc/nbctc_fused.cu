@@ -20,6 +20,12 @@
 #include "fused_kernel.cuh"
 
 namespace nbctc {
+#ifdef NBCTC_PROF
+namespace fused { __device__ long long* g_nbctc_prof = nullptr; }
+extern "C" int nbctc_debug_set_prof(long long* dev_buf) {
+  return (int)cudaMemcpyToSymbol(fused::g_nbctc_prof, &dev_buf, sizeof(dev_buf));
+}
+#endif
 namespace {
 
 struct Plan {
