@@ -54,8 +54,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdr_time = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     flags = [f for f in NVCC_FLAGS if f != "--shared"] + os.environ.get("NBCTC_EXTRA_NVCC_FLAGS", "").split()
-    if "-DNBCTC_PROF" in flags:
-        flags.append("-rdc=true")
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -73,8 +71,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, err in results:
             print(err, file=sys.stderr)
     cmd = [_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp", *[o for o, _ in results]]
-    if "-DNBCTC_PROF" in flags:
-        cmd.insert(1, "-rdc=true")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)

@@ -56,10 +56,12 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 size_t generic_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream);
 
-// fused path (single kernel: row stream -> alpha, beta -> gradient)
+// fused path (single block-streaming kernel: row stream -> alpha, beta -> gradient; nbctc_stream.cu)
 bool fused_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary);
 size_t fused_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary);
 int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream);
+bool fused_pointers_ok(const Problem& p);  // logits / grad 16-byte aligned (the bulk copies need it)
+extern long long* g_stream_prof;           // role-profiler buffer (-DNBCTC_PROF builds), else null
 
 // deterministic reduction of the per-sequence losses (float64, fixed order)
 int reduce_loss_launch(const Problem& p, cudaStream_t stream);

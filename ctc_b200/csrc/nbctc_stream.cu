@@ -1,0 +1,175 @@
+// Fused no-blank CTC forward+backward for sm_100a: ONE kernel reads the logits from HBM once, re-reads them
+// from L2 for the backward half, writes the gradient once, and keeps everything in between on chip
+// (kernel in stream_kernel.cuh).
+//
+//   * a CTA owns GB batch-adjacent sequences; their rows at one time step are contiguous in (T,B,C), so the
+//     producer thread moves a tile of TT time steps with TT TMA bulk copies (HBM -> shared-memory ring) and
+//     the finished gradient tile with TT TMA bulk stores (ring -> HBM).  Phase 1 walks the tiles upwards with
+//     an L2 evict_last policy, phase 2 walks them downwards (most recently read rows first -> L2 hits).
+//   * row warps: row log-partition (NoBlankCTC.py:136) + per-state emission gather (NoBlankCTC.py:96-102)
+//     ahead of the chain; w*(softmax - scatter(gamma)) in place in the ring slot behind it.
+//   * one chain warp per sequence runs the lattice recursions (NoBlankCTC.py:71-87) in the LINEAR domain in
+//     float64 with exact power-of-two rescaling once per tile: a step is a shuffle, an add and a multiply, and
+//     sum_s alpha_t(s) beta_t(s) = Z holds to 1e-13 so gamma needs no per-row normalisation.  Phase 1 stores
+//     one alpha checkpoint per tile; phase 2 replays alpha inside the tile next to the beta recursion (the
+//     reference's backward pass is commented out at NoBlankCTC.py:113-125; autograd does it).
+//   * the three roles advance in lock step, one __syncthreads() per tile; nobody polls.
+//
+// This file: shape -> launch plan (states per lane, lanes per row, group size, shared-memory carve-up),
+// workspace, dispatch.  Algorithmic HBM bytes per sequence: 2*4*T*C (+ labels); per real lattice cell 8*C/mean(L).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "stream_kernel.cuh"
+
+namespace nbctc {
+long long* g_stream_prof = nullptr;
+namespace {
+
+struct Plan {
+  bool ok;
+  StreamCfg cfg;
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  Plan pl{};
+  pl.ok = false;
+  if (Lmax > 256 || T > ((int64_t)1 << 28) || C > ((int64_t)1 << 22)) return pl;
+  StreamCfg& c = pl.cfg;
+  c.NS = Lmax <= 32 ? 2 : Lmax <= 64 ? 4 : Lmax <= 128 ? 8 : 16;  // 16 chain lanes per direction
+  c.Lpad = 16 * c.NS;
+  c.TT = c.NS >= 16 ? 4 : 8;
+  const int PS = c.Lpad + 8, AS = c.Lpad + 8;
+  // chunks per row: with C % 4 == 0 every row starts on a 16-byte boundary, otherwise at any of the 4 phases
+  const int64_t nch = (C % 4 == 0) ? C / 4 : (3 + C + 3) / 4;
+  c.NSEG = 1;
+  if (nch <= 16) {
+    c.LPR = 4;
+    c.CPL = (int)((nch + 3) / 4);
+  } else if (nch <= 64) {
+    c.LPR = 8;
+    c.CPL = (int)std::max<int64_t>(3, (nch + 7) / 8);
+  } else {
+    c.LPR = 32;
+    c.CPL = nch <= 96 ? 3 : nch <= 128 ? 4 : nch <= 192 ? 6 : 8;
+    c.NSEG = (int)((nch + 32 * c.CPL - 1) / (32 * c.CPL));
+  }
+  c.NTmax = (int)((T + c.TT - 1) / c.TT);
+  c.Tpad = (int)align_up((size_t)T, 4);
+  const size_t cap = 227 * 1024;
+  auto layout = [&](int gb, int nrw, int nslot, bool ck_glob, bool lse_glob) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
+    c.GB = gb; c.NRW = nrw; c.NSLOT = nslot; c.ckpt_global = ck_glob; c.lse_global = lse_glob;
+    c.RSg = (int)align_up((size_t)gb * C * 4, 16) + 32;
+    c.o_bar = take(sizeof(uint64_t) * kMaxSlot);
+    c.o_info = take(sizeof(int) * 4 * kMaxGB);
+    c.o_lab = take(sizeof(int) * gb * c.Lpad);
+    c.o_lse = take(lse_glob ? 16 : sizeof(float) * gb * c.Tpad);
+    c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)gb * c.NTmax * c.Lpad);
+    c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
+    c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * c.TT * PS);
+    c.o_ab = take(sizeof(double) * 2 * (size_t)gb * 2 * c.TT * AS);
+    c.o_s2 = take(sizeof(double) * 2 * gb);
+    off = align_up(off, 128);
+    c.o_ring = take((size_t)nslot * c.TT * c.RSg);
+    c.smem_bytes = (uint32_t)off;
+    return off;
+  };
+  // Group size: as many sequences per CTA as the shared memory of one SM takes with a 6-deep ring, checkpoints
+  // and row constants on chip; then the same with the checkpoints / row constants in the workspace; a shallower
+  // ring last.  NBCTC_GB / NBCTC_NRW / NBCTC_NSLOT / NBCTC_CTAS override the search (tuning).
+  const int want_gb = env_int("NBCTC_GB", 0), want_nrw = env_int("NBCTC_NRW", 0), want_slot = env_int("NBCTC_NSLOT", 0);
+  const int ctas = std::max(1, env_int("NBCTC_CTAS", 1));  // CTAs that should share an SM
+  bool placed = false;
+  for (int pass = 0; pass < 3 && !placed; ++pass) {
+    const bool ckg = pass >= 1, lsg = pass >= 2;
+    for (int gb = kMaxGB; gb >= 1 && !placed; gb >>= 1) {
+      if (want_gb && gb != want_gb) continue;
+      if (!want_gb && gb > 1 && (int64_t)gb > B) continue;
+      const int nrw = want_nrw ? want_nrw : (gb == 4 ? 8 : gb == 2 ? 8 : 4);
+      if (nrw % gb != 0 || nrw > kMaxRowWarps) continue;
+      for (int nslot = want_slot ? want_slot : 6; nslot >= (want_slot ? want_slot : 4) && !placed; --nslot)
+        if (layout(gb, nrw, nslot, ckg, lsg) <= cap / ctas) placed = true;
+    }
+  }
+  if (!placed) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+size_t plan_ws_bytes(const Plan& pl, int64_t T, int64_t B) {
+  size_t off = 256;
+  if (!pl.ok) return off;
+  // sized as if both spill to the workspace, so that the plan may differ between the query and the call
+  off = align_up(off + sizeof(double) * (size_t)B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
+  off = align_up(off + sizeof(int) * (size_t)B * pl.cfg.NTmax, 256);
+  off = align_up(off + sizeof(float) * (size_t)B * T, 256);
+  return off;
+}
+
+}  // namespace
+
+bool fused_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary) {
+  if (binary) return false;
+  return make_plan(T, B, C, Lmax).ok;
+}
+
+size_t fused_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary) {
+  (void)binary;
+  Plan a = make_plan(T, B, C, Lmax);
+  if (!a.ok || (!a.cfg.ckpt_global && !a.cfg.lse_global)) return 256;
+  return plan_ws_bytes(a, T, B);
+}
+
+bool fused_pointers_ok(const Problem& p) {
+  // the bulk copies move 16-byte aligned supersets of the rows and the ring keeps the global 16-byte phase
+  return (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0 && (p.grad == nullptr || (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0);
+}
+
+int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (binary) {
+    set_error("fused binary path not available");
+    return NBCTC_ERR_UNSUPPORTED;
+  }
+  Plan pl = make_plan(p.T, p.B, p.C, p.Lmax);
+  if (!pl.ok || !fused_pointers_ok(p)) {
+    set_error("shape or pointer alignment not supported by the fused kernel");
+    return NBCTC_ERR_UNSUPPORTED;
+  }
+  if (pl.cfg.ckpt_global || pl.cfg.lse_global) {
+    const size_t need = plan_ws_bytes(pl, p.T, p.B);
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+      return NBCTC_ERR_WORKSPACE;
+    }
+    char* w = static_cast<char*>(ws);
+    size_t off = 256;
+    pl.cfg.ws_ckpt = reinterpret_cast<double*>(w + off);
+    off = align_up(off + sizeof(double) * (size_t)p.B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
+    pl.cfg.ws_cke = reinterpret_cast<int*>(w + off);
+    off = align_up(off + sizeof(int) * (size_t)p.B * pl.cfg.NTmax, 256);
+    pl.cfg.ws_lse = reinterpret_cast<float*>(w + off);
+  }
+  pl.cfg.prof = g_stream_prof;
+  switch (pl.cfg.NS) {
+    case 2: return launch_stream_ns2(p, pl.cfg, stream);
+    case 4: return launch_stream_ns4(p, pl.cfg, stream);
+    case 8: return launch_stream_ns8(p, pl.cfg, stream);
+    default: return launch_stream_ns16(p, pl.cfg, stream);
+  }
+}
+
+}  // namespace nbctc
+
+// role-profiler hook (only meaningful in -DNBCTC_PROF builds; harmless otherwise)
+extern "C" int nbctc_debug_set_prof(long long* dev_buf) {
+  nbctc::g_stream_prof = dev_buf;
+  return 0;
+}

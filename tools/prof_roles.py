@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Role profiler for the fused kernel (needs a build with NBCTC_EXTRA_NVCC_FLAGS=-DNBCTC_PROF).
-Prints per-role cycle buckets averaged over the CTAs of one cfg-sized launch."""
+"""Role profiler for the block-streaming kernel (needs a build with NBCTC_EXTRA_NVCC_FLAGS=-DNBCTC_PROF).
+Prints per-role cycle buckets, averaged per warp and CTA, for one workload-sized launch.
+Tuning knobs are read by the library from the environment: NBCTC_GB, NBCTC_NRW, NBCTC_NSLOT, NBCTC_CTAS."""
 import ctypes as C
 import os
 import sys
@@ -13,33 +14,61 @@ import bench
 import ctc_b200
 from ctc_b200 import _ffi
 
-w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+w = bench.WORKLOADS[name]
 B, T, Cc, Lmax = w["B"], w["T"], w["C"], w["Lmax"]
+GB = int(os.environ.get("NBCTC_GB", "4"))
+NRW = int(os.environ.get("NBCTC_NRW", "8"))
 dev = torch.device("cuda:0")
 tg, il, tl = bench.make_inputs_np(w, 1234)
 x = torch.randn((T, B, Cc), device=dev)
 tgt, ilt, tlt = torch.tensor(tg, device=dev), torch.tensor(il, device=dev), torch.tensor(tl, device=dev)
 lib = _ffi.lib()
 lib.nbctc_debug_set_prof.argtypes = [C.c_void_p]
-prof = torch.zeros((B, 6, 8), dtype=torch.int64, device=dev)
-assert lib.nbctc_debug_set_prof(prof.data_ptr()) == 0
+prof = torch.zeros(24 + 128 * 16 * 2, dtype=torch.int64, device=dev)
 per = torch.empty(B, device=dev)
 grad = torch.empty_like(x)
 ws_bytes = int(lib.nbctc_workspace_bytes(T, B, Cc, Lmax, 0, 0))
 ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-for it in range(3):
+
+
+def run():
     rc = lib.nbctc_loss_grad_f32(x.data_ptr(), T, B, Cc, tgt.data_ptr(), Lmax, ilt.data_ptr(), tlt.data_ptr(),
                                  per.data_ptr(), None, None, grad.data_ptr(), None, 1.0 / B, ws.data_ptr(), ws_bytes, 0,
                                  torch.cuda.current_stream().cuda_stream)
-    assert rc == 0
+    assert rc == 0, lib.nbctc_last_error()
+
+
+for _ in range(3):
+    run()
 torch.cuda.synchronize()
-p = prof.cpu().numpy().astype(np.float64)
+assert lib.nbctc_debug_set_prof(prof.data_ptr()) == 0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record()
+torch.cuda.synchronize()
+pall = prof.cpu().numpy().astype(np.float64)
+p = pall[:24].reshape(3, 8)
+trace = pall[24:].reshape(128, 16, 2)
+groups = (B + GB - 1) // GB
 names = {
-    "chain": ["wait pfull ph1", "alpha steps", "wait pfull ph2", "beta+replay steps", "wait gempty", "gamma pass", "-", "total"],
-    "row": ["wait slot ph1", "forward tile", "wait slot ph2", "emit tile (A)", "wait gamma", "backward tile (B)", "-", "total"],
-    "producer": ["wait sempty ph1", "wait sempty ph2", "-", "-", "-", "-", "-", "total"],
+    0: ("chain", GB, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
+    1: ("row", NRW, ["wait rows", "forward (LSE+emit)", "emit", "grad", "-", "-", "barrier", "total"]),
+    2: ("producer", 1, ["store issue", "wait store reads", "-", "-", "-", "-", "barrier", "total"]),
 }
-print(f"workload {sys.argv[1] if len(sys.argv) > 1 else 'cfg2'}: mean cycles per CTA (sequence)")
-for role, sl in (("chain", p[:, 0]), ("row", p[:, 1:5].reshape(-1, 8)), ("producer", p[:, 5])):
-    m = sl.mean(axis=0)
-    print(f"  {role:9s} " + "  ".join(f"{n}={v:,.0f}" for n, v in zip(names[role], m) if n != "-"))
+print(f"workload {name}: GB={GB} NRW={NRW} groups={groups} kernel {e0.elapsed_time(e1):.3f} ms (instrumented); "
+      f"mean cycles per warp per CTA")
+for role, (rn, nw, nm) in names.items():
+    m = p[role] / (groups * nw)
+    print(f"  {rn:9s} " + "  ".join(f"{n}={v:,.0f}" for n, v in zip(nm, m) if n != "-"))
+
+# per-iteration trace of the middle CTA: cycles each role spends working in the iteration (work end - previous barrier end)
+nw = GB + NRW + 1
+prev = np.zeros(nw)
+print("trace of one CTA: it | iteration cycles | busy cycles chain(max) rows(max) producer")
+for itx in range(128):
+    if trace[itx, :nw, 1].max() == 0:
+        break
+    busy = trace[itx, :nw, 0] - prev
+    end = trace[itx, :nw, 1]
+    print(f"  it={itx - 1:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f} prod={busy[GB + NRW]:6.0f}")
+    prev = end
