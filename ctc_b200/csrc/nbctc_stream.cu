@@ -38,67 +38,68 @@ int env_int(const char* name, int dflt) {
 }
 
 Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  (void)B;
   Plan pl{};
   pl.ok = false;
-  if (Lmax > 256 || T > ((int64_t)1 << 28) || C > ((int64_t)1 << 22)) return pl;
+  // C >= 4: a 16-byte chunk of a slab then touches at most two rows (grad_step)
+  if (Lmax > 256 || T > ((int64_t)1 << 28) || C > ((int64_t)1 << 22) || C < 4) return pl;
   StreamCfg& c = pl.cfg;
   c.NS = Lmax <= 32 ? 2 : Lmax <= 64 ? 4 : Lmax <= 128 ? 8 : 16;  // 16 chain lanes per direction
   c.Lpad = 16 * c.NS;
   c.TT = c.NS >= 16 ? 4 : 8;
   const int PS = c.Lpad + 8, AS = c.Lpad + 8;
+  const int PSEQ = c.TT * PS + 8, ABSEQ = 2 * c.TT * AS + 8;
   // chunks per row: with C % 4 == 0 every row starts on a 16-byte boundary, otherwise at any of the 4 phases
   const int64_t nch = (C % 4 == 0) ? C / 4 : (3 + C + 3) / 4;
+  // lanes per row (LPR) fixes the sequences per CTA (GB = 32 / LPR).  NBCTC_LPR / NBCTC_CTAS override (tuning).
+  const int want_lpr = env_int("NBCTC_LPR", 0);
+  c.ctas_per_sm = std::max(1, env_int("NBCTC_CTAS", 1));
   c.NSEG = 1;
-  if (nch <= 16) {
-    c.LPR = 4;
+  c.LPR = want_lpr ? want_lpr : nch <= 16 ? 4 : nch <= 64 ? 8 : 32;
+  if (c.LPR == 4) {
     c.CPL = (int)((nch + 3) / 4);
-  } else if (nch <= 64) {
-    c.LPR = 8;
+    if (c.CPL > 4) return pl;
+  } else if (c.LPR == 8) {
     c.CPL = (int)std::max<int64_t>(3, (nch + 7) / 8);
-  } else {
-    c.LPR = 32;
+    if (c.CPL > 8) return pl;
+  } else if (c.LPR == 16) {
+    c.CPL = (int)std::max<int64_t>(2, (nch + 15) / 16);
+    if (c.CPL > 4) return pl;
+  } else if (c.LPR == 32) {
     c.CPL = nch <= 96 ? 3 : nch <= 128 ? 4 : nch <= 192 ? 6 : 8;
     c.NSEG = (int)((nch + 32 * c.CPL - 1) / (32 * c.CPL));
+  } else {
+    return pl;
   }
+  c.GB = 32 / c.LPR;
   c.NTmax = (int)((T + c.TT - 1) / c.TT);
   c.Tpad = (int)align_up((size_t)T, 4);
-  const size_t cap = 227 * 1024;
-  auto layout = [&](int gb, int nrw, int nslot, bool ck_glob, bool lse_glob) {
+  const size_t cap = (size_t)(c.ctas_per_sm >= 2 ? 113 : 227) * 1024;
+  auto layout = [&](bool ck_glob, bool lse_glob) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
-    c.GB = gb; c.NRW = nrw; c.NSLOT = nslot; c.ckpt_global = ck_glob; c.lse_global = lse_glob;
+    const int gb = c.GB;
+    c.ckpt_global = ck_glob; c.lse_global = lse_glob;
     c.RSg = (int)align_up((size_t)gb * C * 4, 16) + 32;
-    c.o_bar = take(sizeof(uint64_t) * kMaxSlot);
+    c.o_bar = take(sizeof(uint64_t) * 8);
     c.o_info = take(sizeof(int) * 4 * kMaxGB);
     c.o_lab = take(sizeof(int) * gb * c.Lpad);
     c.o_lse = take(lse_glob ? 16 : sizeof(float) * gb * c.Tpad);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)gb * c.NTmax * c.Lpad);
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
-    c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * c.TT * PS);
-    c.o_ab = take(sizeof(double) * 2 * (size_t)gb * 2 * c.TT * AS);
+    c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * PSEQ);
+    c.o_ab = take(sizeof(double) * 2 * (size_t)gb * ABSEQ);
     c.o_s2 = take(sizeof(double) * 2 * gb);
+    c.o_tab = take(sizeof(float) * 2 * (size_t)c.TT * (kMaxGB + 1));
     off = align_up(off, 128);
-    c.o_ring = take((size_t)nslot * c.TT * c.RSg);
+    c.o_ring = take((size_t)kNSlot * c.TT * c.RSg);
     c.smem_bytes = (uint32_t)off;
     return off;
   };
-  // Group size: as many sequences per CTA as the shared memory of one SM takes with a 6-deep ring, checkpoints
-  // and row constants on chip; then the same with the checkpoints / row constants in the workspace; a shallower
-  // ring last.  NBCTC_GB / NBCTC_NRW / NBCTC_NSLOT / NBCTC_CTAS override the search (tuning).
-  const int want_gb = env_int("NBCTC_GB", 0), want_nrw = env_int("NBCTC_NRW", 0), want_slot = env_int("NBCTC_NSLOT", 0);
-  const int ctas = std::max(1, env_int("NBCTC_CTAS", 1));  // CTAs that should share an SM
+  // checkpoints and row constants on chip if they fit next to the ring, else in the workspace
   bool placed = false;
-  for (int pass = 0; pass < 3 && !placed; ++pass) {
-    const bool ckg = pass >= 1, lsg = pass >= 2;
-    for (int gb = kMaxGB; gb >= 1 && !placed; gb >>= 1) {
-      if (want_gb && gb != want_gb) continue;
-      if (!want_gb && gb > 1 && (int64_t)gb > B) continue;
-      const int nrw = want_nrw ? want_nrw : (gb == 4 ? 8 : gb == 2 ? 8 : 4);
-      if (nrw % gb != 0 || nrw > kMaxRowWarps) continue;
-      for (int nslot = want_slot ? want_slot : 6; nslot >= (want_slot ? want_slot : 4) && !placed; --nslot)
-        if (layout(gb, nrw, nslot, ckg, lsg) <= cap / ctas) placed = true;
-    }
-  }
+  for (int pass = 0; pass < 3 && !placed; ++pass)
+    if (layout(pass >= 1, pass >= 2) <= cap) placed = true;
   if (!placed) return pl;
   pl.ok = true;
   return pl;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Role profiler for the block-streaming kernel (needs a build with NBCTC_EXTRA_NVCC_FLAGS=-DNBCTC_PROF).
 Prints per-role cycle buckets, averaged per warp and CTA, for one workload-sized launch.
-Tuning knobs are read by the library from the environment: NBCTC_GB, NBCTC_NRW, NBCTC_NSLOT, NBCTC_CTAS."""
+Tuning knobs are read by the library from the environment: NBCTC_LPR, NBCTC_CTAS."""
 import ctypes as C
 import os
 import sys
@@ -17,15 +17,16 @@ from ctc_b200 import _ffi
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w = bench.WORKLOADS[name]
 B, T, Cc, Lmax = w["B"], w["T"], w["C"], w["Lmax"]
-GB = int(os.environ.get("NBCTC_GB", "4"))
-NRW = int(os.environ.get("NBCTC_NRW", "8"))
+LPR = int(os.environ.get("NBCTC_LPR", "8"))
+GB = 32 // LPR
+NRW = 8
 dev = torch.device("cuda:0")
 tg, il, tl = bench.make_inputs_np(w, 1234)
 x = torch.randn((T, B, Cc), device=dev)
 tgt, ilt, tlt = torch.tensor(tg, device=dev), torch.tensor(il, device=dev), torch.tensor(tl, device=dev)
 lib = _ffi.lib()
 lib.nbctc_debug_set_prof.argtypes = [C.c_void_p]
-prof = torch.zeros(24 + 128 * 16 * 2, dtype=torch.int64, device=dev)
+prof = torch.zeros(24 + 128 * 32 * 2, dtype=torch.int64, device=dev)
 per = torch.empty(B, device=dev)
 grad = torch.empty_like(x)
 ws_bytes = int(lib.nbctc_workspace_bytes(T, B, Cc, Lmax, 0, 0))
@@ -48,12 +49,12 @@ e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 pall = prof.cpu().numpy().astype(np.float64)
 p = pall[:24].reshape(3, 8)
-trace = pall[24:].reshape(128, 16, 2)
+trace = pall[24:].reshape(128, 32, 2)
 groups = (B + GB - 1) // GB
 names = {
     0: ("chain", GB, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
     1: ("row", NRW, ["wait rows", "forward (LSE+emit)", "emit", "grad", "-", "-", "barrier", "total"]),
-    2: ("producer", 1, ["store issue", "wait store reads", "-", "-", "-", "-", "barrier", "total"]),
+    2: ("producer", 1, ["store issue", "wait store reads", "load issue", "-", "-", "-", "barrier", "total"]),
 }
 print(f"workload {name}: GB={GB} NRW={NRW} groups={groups} kernel {e0.elapsed_time(e1):.3f} ms (instrumented); "
       f"mean cycles per warp per CTA")
