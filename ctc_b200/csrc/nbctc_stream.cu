@@ -1,19 +1,18 @@
-// Fused no-blank CTC forward+backward for sm_100a: ONE kernel reads the logits from HBM once, re-reads them
-// from L2 for the backward half, writes the gradient once, and keeps everything in between on chip
-// (kernel in stream_kernel.cuh).
+// Fused no-blank CTC forward+backward for sm_100a: ONE kernel reads the logits from HBM once, writes the
+// gradient once, and keeps everything in between on chip or in L2 (kernel in stream_kernel.cuh).
 //
-//   * a CTA owns GB batch-adjacent sequences; their rows at one time step are contiguous in (T,B,C), so the
-//     producer thread moves a tile of TT time steps with TT TMA bulk copies (HBM -> shared-memory ring) and
-//     the finished gradient tile with TT TMA bulk stores (ring -> HBM).  Phase 1 walks the tiles upwards with
-//     an L2 evict_last policy, phase 2 walks them downwards (most recently read rows first -> L2 hits).
-//   * row warps: row log-partition (NoBlankCTC.py:136) + per-state emission gather (NoBlankCTC.py:96-102)
-//     ahead of the chain; w*(softmax - scatter(gamma)) in place in the ring slot behind it.
+//   * a CTA owns GB batch-adjacent sequences; their rows at one time step are contiguous in (T,B,C) ("slab").
+//     Row warp w owns time step w of every tile of TT steps: one TMA bulk copy brings its slab into a
+//     shared-memory ring, the warp computes the row log-partitions (NoBlankCTC.py:136), turns the slab into
+//     w*softmax in place, gathers the per-state emissions (NoBlankCTC.py:96-102) and sends the slab to the
+//     gradient tensor with one TMA bulk store.
 //   * one chain warp per sequence runs the lattice recursions (NoBlankCTC.py:71-87) in the LINEAR domain in
 //     float64 with exact power-of-two rescaling once per tile: a step is a shuffle, an add and a multiply, and
 //     sum_s alpha_t(s) beta_t(s) = Z holds to 1e-13 so gamma needs no per-row normalisation.  Phase 1 stores
-//     one alpha checkpoint per tile; phase 2 replays alpha inside the tile next to the beta recursion (the
-//     reference's backward pass is commented out at NoBlankCTC.py:113-125; autograd does it).
-//   * the three roles advance in lock step, one __syncthreads() per tile; nobody polls.
+//     one alpha checkpoint per tile; phase 2 walks the tiles downwards, replays alpha inside the tile next to
+//     the beta recursion (the reference's backward pass is commented out at NoBlankCTC.py:113-125; autograd
+//     does it), and the row warps add -w*gamma to the gradient rows with global float reductions.
+//   * the two roles advance in lock step, one __syncthreads() per tile; nobody polls.
 //
 // This file: shape -> launch plan (states per lane, lanes per row, group size, shared-memory carve-up),
 // workspace, dispatch.  Algorithmic HBM bytes per sequence: 2*4*T*C (+ labels); per real lattice cell 8*C/mean(L).
@@ -73,33 +72,30 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   }
   c.GB = 32 / c.LPR;
   c.NTmax = (int)((T + c.TT - 1) / c.TT);
-  c.Tpad = (int)align_up((size_t)T, 4);
   const size_t cap = (size_t)(c.ctas_per_sm >= 2 ? 113 : 227) * 1024;
-  auto layout = [&](bool ck_glob, bool lse_glob) {
+  auto layout = [&](bool ck_glob) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
     const int gb = c.GB;
-    c.ckpt_global = ck_glob; c.lse_global = lse_glob;
+    c.ckpt_global = ck_glob;
     c.RSg = (int)align_up((size_t)gb * C * 4, 16) + 32;
-    c.o_bar = take(sizeof(uint64_t) * 8);
-    c.o_info = take(sizeof(int) * 4 * kMaxGB);
+    c.o_bar = take(sizeof(uint64_t) * kNSlot * c.TT);
+    c.o_info = take(sizeof(int) * 3 * kMaxGB);
     c.o_lab = take(sizeof(int) * gb * c.Lpad);
-    c.o_lse = take(lse_glob ? 16 : sizeof(float) * gb * c.Tpad);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)gb * c.NTmax * c.Lpad);
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
     c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * PSEQ);
-    c.o_ab = take(sizeof(double) * 2 * (size_t)gb * ABSEQ);
     c.o_s2 = take(sizeof(double) * 2 * gb);
-    c.o_tab = take(sizeof(float) * 2 * (size_t)c.TT * (kMaxGB + 1));
     off = align_up(off, 128);
-    c.o_ring = take((size_t)kNSlot * c.TT * c.RSg);
+    // the ring (phase 1) and the alpha/beta tiles (phase 2) share one region
+    c.o_ring = take(std::max((size_t)kNSlot * c.TT * c.RSg, sizeof(double) * 2 * (size_t)gb * ABSEQ));
     c.smem_bytes = (uint32_t)off;
     return off;
   };
-  // checkpoints and row constants on chip if they fit next to the ring, else in the workspace
+  // checkpoints on chip if they fit next to the ring, else in the workspace
   bool placed = false;
-  for (int pass = 0; pass < 3 && !placed; ++pass)
-    if (layout(pass >= 1, pass >= 2) <= cap) placed = true;
+  for (int pass = 0; pass < 2 && !placed; ++pass)
+    if (layout(pass >= 1) <= cap) placed = true;
   if (!placed) return pl;
   pl.ok = true;
   return pl;
@@ -108,10 +104,9 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
 size_t plan_ws_bytes(const Plan& pl, int64_t T, int64_t B) {
   size_t off = 256;
   if (!pl.ok) return off;
-  // sized as if both spill to the workspace, so that the plan may differ between the query and the call
+  (void)T;
   off = align_up(off + sizeof(double) * (size_t)B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
   off = align_up(off + sizeof(int) * (size_t)B * pl.cfg.NTmax, 256);
-  off = align_up(off + sizeof(float) * (size_t)B * T, 256);
   return off;
 }
 
@@ -125,8 +120,8 @@ bool fused_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary)
 size_t fused_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary) {
   (void)binary;
   Plan a = make_plan(T, B, C, Lmax);
-  if (!a.ok || (!a.cfg.ckpt_global && !a.cfg.lse_global)) return 256;
-  return plan_ws_bytes(a, T, B);
+  if (!a.ok) return 256;
+  return plan_ws_bytes(a, T, B);  // sized for checkpoints in the workspace whatever the plan (NBCTC_CTAS may differ)
 }
 
 bool fused_pointers_ok(const Problem& p) {
@@ -144,7 +139,7 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
     set_error("shape or pointer alignment not supported by the fused kernel");
     return NBCTC_ERR_UNSUPPORTED;
   }
-  if (pl.cfg.ckpt_global || pl.cfg.lse_global) {
+  if (pl.cfg.ckpt_global) {
     const size_t need = plan_ws_bytes(pl, p.T, p.B);
     if (ws == nullptr || ws_bytes < need) {
       set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -155,8 +150,6 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
     pl.cfg.ws_ckpt = reinterpret_cast<double*>(w + off);
     off = align_up(off + sizeof(double) * (size_t)p.B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
     pl.cfg.ws_cke = reinterpret_cast<int*>(w + off);
-    off = align_up(off + sizeof(int) * (size_t)p.B * pl.cfg.NTmax, 256);
-    pl.cfg.ws_lse = reinterpret_cast<float*>(w + off);
   }
   pl.cfg.prof = g_stream_prof;
   switch (pl.cfg.NS) {

@@ -1,23 +1,30 @@
 // Block-streaming no-blank CTC forward+backward kernel for sm_100a (overview in nbctc_stream.cu).
 //
 // One CTA owns a GROUP of GB = 32/LPR batch-adjacent sequences and walks their lattice in tiles of TT time steps.
-// The rows (t, b0..b0+GB) of one time step are contiguous in the (T,B,C) tensor ("slab"), so a tile is TT bulk
-// copies of GB*C*4 bytes.  The CTA runs a lock-step software pipeline over "items" (item i < NT: phase-1 tile i,
-// walking up; item i >= NT: phase-2 tile 2NT-1-i, walking down), one __syncthreads() per iteration, no polling:
+// The rows (t, b0..b0+GB) of one time step are contiguous in the (T,B,C) tensor ("slab").  Row warp w owns time
+// step w of every tile: it moves its slab with TMA bulk copies (global -> ring slot -> global) and no other warp
+// ever touches it.  Chain warp r owns sequence r.  The two roles meet in small shared-memory tiles and advance
+// in lock step, one __syncthreads() per tile, nobody polls.
 //
-//   iteration `it`:   producer warp     lane i moves time step i of a tile: TMA bulk store of item it-2's gradient
-//                                       rows; TMA bulk loads of the items ahead (as far as ring slots are free)
-//                                       with an L2 evict_last policy in phase 1 (phase 2 re-reads hit L2)
-//                     row warps         warp w = time step w of the tile, lane group = sequence.  Item it+1: row
-//                                       log-partition + emission gather (phase 1, NoBlankCTC.py:136,:96-102) or
-//                                       emission gather only (phase 2); item it-1: w*softmax over the whole slab
-//                                       in place in the ring slot, then scatter of -w*gamma
-//                     chain warps       item it: one warp per sequence, 16 lanes x NS states in float64, linear
-//                                       domain with exact power-of-two rescaling per tile (NoBlankCTC.py:71-87).
-//                                       Phase 1: alpha + one checkpoint per tile.  Phase 2: lanes 0-15 replay
-//                                       alpha inside the tile from the checkpoint while lanes 16-31 run beta in
-//                                       the same instructions (beta is kept in reversed state order).
+//   phase 1 (tiles upwards)    row warps    slab of item it+1: row log-partition (NoBlankCTC.py:136), then the slab
+//                                           becomes w*softmax(x) IN PLACE (the exponentials of the log-partition
+//                                           are reused) and goes to the gradient tensor with one bulk store;
+//                                           emissions p_t(s) = softmax(x_t)[label_s] (NoBlankCTC.py:96-102) are
+//                                           gathered from the finished slab -> p-tile
+//                              chain warps  item it: alpha over the tile (NoBlankCTC.py:71-87), 16 lanes x NS
+//                                           states in float64, linear domain, exact power-of-two rescaling and one
+//                                           checkpoint per tile
+//   phase 2 (tiles downwards)  row warps    item it+1: the same emissions again, gathered from the gradient rows
+//                                           written in phase 1 (L2 hits; bit-identical to phase 1);
+//                                           item it-1: gamma = alpha*beta/Z from the chain's tiles, -w*gamma added
+//                                           to the gradient rows with global float reductions (repeated labels
+//                                           accumulate)
+//                              chain warps  item it: lanes 0-15 replay alpha inside the tile from the checkpoint
+//                                           while lanes 16-31 run beta in the same instructions (beta is kept in
+//                                           reversed state order)
 //
+// HBM traffic: the logits are read once, the gradient is written once; the phase-2 gathers / reductions touch
+// lines that were written a few microseconds earlier by the same SM.
 // Template parameters: NS (chain states per lane, Lmax <= 16*NS), LPR (lanes per row; GB = 32/LPR sequences per
 // CTA), CPL (16-byte chunks per lane and row segment).
 #pragma once
@@ -29,7 +36,7 @@
 namespace nbctc {
 
 constexpr int kMaxGB = 8;   // sequences per group upper bound (LPR = 4)
-constexpr int kNSlot = 6;   // ring depth (tiles)
+constexpr int kNSlot = 4;   // ring depth (tiles): two loading, one being worked on, one draining
 
 struct StreamCfg {
   int NS, Lpad, TT;
@@ -37,14 +44,12 @@ struct StreamCfg {
   int GB;     // sequences per group (CTA) = 32 / LPR
   int RSg;    // bytes per time step in a ring slot: round16(GB*C*4) + 32
   int NTmax;  // ceil(T / TT)
-  int Tpad;   // lse row stride (floats)
-  int ckpt_global, lse_global;
+  int ckpt_global;
   int ctas_per_sm;
-  uint32_t o_bar, o_info, o_lab, o_lse, o_ckpt, o_cke, o_ptile, o_ab, o_s2, o_tab, o_ring, smem_bytes;
+  uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
   int* ws_cke;      // [B][NTmax]
-  float* ws_lse;    // [B][T]
-  long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [128][32][2] trace
+  long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [160][32][2] trace
 };
 
 template <int NS, int LPR>
@@ -58,7 +63,7 @@ struct Geo {
   static constexpr int AS = Lpad + 8;          // alpha/beta tile row stride (doubles)
   static constexpr int PSEQ = TT * PS + 8;     // p-tile floats per sequence (+8: lane groups hit distinct banks)
   static constexpr int ABSEQ = 2 * TT * AS + 8;  // alpha+beta tile doubles per sequence
-  static constexpr int NTHREADS = 32 * (GB + NRW + 1);
+  static constexpr int NTHREADS = 32 * (GB + NRW);
 };
 
 int launch_stream_ns2(const Problem& p, const StreamCfg& cfg, cudaStream_t stream);
@@ -72,10 +77,6 @@ namespace stream {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kPMin = 7.52316385e-37f;  // 2^-120: emission floor (8 steps stay inside the f64 range)
 constexpr float kNegInf = -INFINITY;
-// label slots in shared memory / registers: class index in the low 22 bits, above it the state's rank among the
-// earlier states with the same class (the gamma scatter runs one conflict-free round per rank); -1 = no state
-constexpr int kLabBits = 22;
-constexpr int kLabMask = (1 << kLabBits) - 1;
 
 // ---------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,8 +86,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -142,6 +143,7 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -174,17 +176,15 @@ __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the
 #endif
 
 struct Smem {
-  uint64_t* sfull;  // [kNSlot] ring-slot "rows have landed" barriers
-  int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags, [3*kMaxGB..) largest duplicate rank
+  uint64_t* sfull;  // [kNSlot][TT] "this time step's slab has landed" barriers
+  int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags
   int* lab;         // [GB][Lpad]
-  float* lse;       // [GB][Tpad]
-  double* ckpt;     // [GB][NTmax][Lpad]
+  double* ckpt;     // [GB][NTmax][Lpad]   (or in the workspace)
   int* cke;         // [GB][NTmax]
   float* ptile;     // [2][GB][PSEQ]
-  double* ab;       // [2][GB][ABSEQ]
   double* s2;       // [2][GB]
-  float2* tab;      // [NRW][kMaxGB + 1] per row warp: (lse*log2e, w) of the slab's rows
-  unsigned char* ring;
+  unsigned char* ring;  // [kNSlot][TT][RSg] in phase 1
+  double* ab;       // [2][GB][ABSEQ] in phase 2 (same memory as the ring)
 };
 
 // ============================================================================ chain warp
@@ -304,16 +304,16 @@ __device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int
   }
 }
 
-// ---- phase 2, tile k: beta (lanes 16-31) + alpha replay (lanes 0-15); alpha_t(s), beta_t(s) -> ab tile
+// ---- phase 2, tile k: beta (lanes 16-31) + alpha replay (lanes 0-15) from the checkpoint (ckv, exponent EaK;
+// unused for k = 0); alpha_t(s), beta_t(s) -> ab tile
 template <int NS, int TT, int PS, int AS>
-__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, int Tb, const double* ck, const int* cke,
+__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, int Tb, const double (&ckv)[NS], int EaK,
                                              int k, const float* __restrict__ pt, double* __restrict__ abt, double* s2_out) {
   constexpr int Lpad = 16 * NS;
   const int hl = lane & 15;
   const bool isb = lane >= 16;
   double sum[NS];
   // gamma = alpha * beta * w / Z; the power-of-two part is split over both factors (range safety)
-  const int EaK = (k == 0) ? 0 : cke[k];
   const int Eb_all = __shfl_sync(0xffffffffu, c.Eb, 16);
   const int d = EaK + Eb_all - c.Ez;
   const double s1 = pow2i(d / 2);
@@ -326,7 +326,7 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
       c.carry = (lane == 0) ? s1 : 0.0;
     } else {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) x[j] = ck[(k * NS + j) * 16] * s1;  // exact: alpha replay runs pre-scaled
+      for (int j = 0; j < NS; ++j) x[j] = ckv[j] * s1;  // exact: alpha replay runs pre-scaled
     }
   }
   const int nv = min(TT, Tb - k * TT);
@@ -362,9 +362,9 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
 }
 
 // ============================================================================ row warps
-// Geometry of one (t,b) row seen as 16-byte chunks of the ring slot: the row starts `off4` floats into chunk 0
-// and ends `rem` floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0, and neighbouring
-// sequences of the group share their boundary chunks).
+// Geometry of one (t,b) row seen as 16-byte chunks of its slab: the row starts `off4` floats into chunk 0 and ends
+// `rem` floats into chunk nch-1 (rows are only 4-byte aligned when C % 4 != 0, and neighbouring sequences of the
+// group share their boundary chunks).
 struct RowGeom {
   float4* srow;
   int off4, nch, rem;  // rem in 1..4 = valid floats in the last chunk
@@ -379,8 +379,17 @@ __device__ __forceinline__ void mask_tail(float4& v, int rem) {
   if (rem < 3) v.z = kNegInf;
   if (rem < 2) v.y = kNegInf;
 }
+// floats [lo, hi) of a chunk (a boundary chunk belongs to two rows, i.e. two lane groups)
+__device__ __forceinline__ void store_part(float4* dst, const float4& y, int lo, int hi) {
+  float* e = reinterpret_cast<float*>(dst);
+  if (lo <= 0 && hi > 0) e[0] = y.x;
+  if (lo <= 1 && hi > 1) e[1] = y.y;
+  if (lo <= 2 && hi > 2) e[2] = y.z;
+  if (lo <= 3 && hi > 3) e[3] = y.w;
+}
+__device__ __forceinline__ float4 scale4(const float4& v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
 
-// One row warp = one time step of every tile; lane group gi (LPR lanes) = sequence gi of the CTA's group.
+// One row warp = one time step of every tile; lane group (LPR lanes) = one sequence of the CTA's group.
 template <int NS, int LPR, int CPL>
 struct Rows {
   using G = Geo<NS, LPR>;
@@ -390,25 +399,24 @@ struct Rows {
 
   const Problem& P;
   const StreamCfg& cfg;
+  const Smem& S;
   const int lane, li, seq;  // seq = lane group = sequence of the group
   const int ti;             // this warp's time step inside a tile
   const int gcnt;
   const int64_t b0;
   const int Tb, Lb, C;
-  const int max_rank;
-  float* lse_seq;
+  const uint32_t gbytes;    // bytes of the group's rows at one time step
+  const float wgt;          // gradient weight of the sequence; weff = wgt, or 1 where wgt == 0 (see kernel tail)
+  const float weff, winv;
   const int* lab_seq;
-  float2* tab;
-  const int* info;
   int labr[kLabRegs ? NSL : 1];  // this lane's labels (-1 = no state)
 
   __device__ __forceinline__ Rows(const Problem& P_, const StreamCfg& cfg_, const Smem& S_, int lane_, int ti_, int gcnt_,
-                                  int64_t b0_)
-      : P(P_), cfg(cfg_), lane(lane_), li(lane_ & (LPR - 1)), seq(lane_ / LPR), ti(ti_), gcnt(gcnt_), b0(b0_),
-        Tb(S_.info[lane_ / LPR]), Lb(S_.info[kMaxGB + lane_ / LPR]), C((int)P_.C), max_rank(S_.info[3 * kMaxGB + lane_ / LPR]),
-        lse_seq(cfg_.lse_global ? cfg_.ws_lse + (size_t)min(b0_ + lane_ / LPR, P_.B - 1) * P_.T
-                                : S_.lse + (size_t)(lane_ / LPR) * cfg_.Tpad),
-        lab_seq(S_.lab + (lane_ / LPR) * Lpad), tab(S_.tab + ti_ * (kMaxGB + 1)), info(S_.info) {
+                                  int64_t b0_, float wgt_)
+      : P(P_), cfg(cfg_), S(S_), lane(lane_), li(lane_ & (LPR - 1)), seq(lane_ / LPR), ti(ti_), gcnt(gcnt_), b0(b0_),
+        Tb(S_.info[lane_ / LPR]), Lb(S_.info[kMaxGB + lane_ / LPR]), C((int)P_.C),
+        gbytes((uint32_t)gcnt_ * (uint32_t)P_.C * 4u), wgt(wgt_), weff(wgt_ != 0.f ? wgt_ : 1.f),
+        winv(1.f / (wgt_ != 0.f ? wgt_ : 1.f)), lab_seq(S_.lab + (lane_ / LPR) * Lpad) {
     if constexpr (kLabRegs) {
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
@@ -423,11 +431,13 @@ struct Rows {
     return st < Lb ? lab_seq[st] : -1;
   }
 
+  __device__ __forceinline__ uint64_t elem_off(int t) const { return (((uint64_t)t * P.B + b0) * P.C) * 4u; }
   // float index (0..3) of the slab's first element inside its first 16-byte chunk (both tensors are 16-byte aligned)
   __device__ __forceinline__ int slab_phase(int t) const {
     return (int)(((((unsigned)t & 3u) * ((unsigned)P.B & 3u) + ((unsigned)b0 & 3u)) * ((unsigned)C & 3u)) & 3u);
   }
-  // this lane group's row at time t; `tsl` = the time step's slab in the ring slot
+  __device__ __forceinline__ unsigned char* slab(int slot) const { return S.ring + ((size_t)slot * TT + ti) * cfg.RSg; }
+  // this lane group's row at time t inside the slab `tsl`
   __device__ __forceinline__ RowGeom geom(int t, unsigned char* tsl) const {
     const int fidx = slab_phase(t) + seq * C;  // float index of the row inside the slab's chunks
     RowGeom g;
@@ -438,27 +448,45 @@ struct Rows {
     return g;
   }
 
-  __device__ __forceinline__ void load_seg(const RowGeom& g, bool act, int seg, float4 (&v)[CPL]) const {
-    const float4* src = g.srow + seg * SEG + li;
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      const int q = seg * SEG + li + c * LPR;
-      v[c] = (act && q < g.nch) ? src[c * LPR] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+  // ---------------------------------------------------------------- TMA (lane 0 only)
+  // logits rows of time step t -> ring slot: 16-byte aligned superset of the slab
+  __device__ __forceinline__ void issue_load(int slot, int t) const {
+    uint64_t* bar = &S.sfull[slot * TT + ti];
+    unsigned char* dst = slab(slot);
+    const uint64_t a = reinterpret_cast<uint64_t>(P.logits) + elem_off(t);
+    const uint64_t lim = reinterpret_cast<uint64_t>(P.logits) + (uint64_t)P.T * P.B * P.C * 4u;
+    const uint64_t a0 = a & ~uint64_t(15);
+    uint64_t a1 = (a + gbytes + 15) & ~uint64_t(15);
+    if (a1 > lim) {
+      // the tensor's last rows end inside a 16-byte chunk: the bulk copy stops before it, the rest goes by hand
+      a1 = lim & ~uint64_t(15);
+      const float* src = reinterpret_cast<const float*>(a1);
+      float* d = reinterpret_cast<float*>(dst + (a1 - a0));
+      const int n = (int)((a + gbytes - a1) >> 2);
+      for (int c = 0; c < n; ++c) d[c] = __ldg(src + c);
+    }
+    if (a1 > a0) {
+      bulk_g2s(smem_u32(dst), a0, (uint32_t)(a1 - a0), smem_u32(bar));
+      mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));  // the phase cannot complete before this arrival
+    } else {
+      mbar_arrive(bar);
     }
   }
-  // elements of the neighbouring rows (head of chunk 0 / tail of chunk nch-1) -> -inf
-  template <bool kSingle>
-  __device__ __forceinline__ void mask_seg(const RowGeom& g, int seg, bool first, bool last, float4 (&v)[CPL]) const {
-    if (first && li == 0) mask_head(v[0], g.off4);
-    if (last) {
-      const int ql = g.nch - 1 - seg * SEG - li;  // tail chunk sits in slot c with c*LPR == ql
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        // with one segment the tail can only be in the last two slots (nch varies by <= 1 between rows)
-        if (kSingle && c + 2 < CPL) continue;
-        if (ql == c * LPR) mask_tail(v[c], g.rem);
-      }
+  // finished slab of time step t -> gradient rows: the 16-byte aligned interior as one bulk store, at most 3
+  // floats on either side by hand
+  __device__ __forceinline__ void issue_store(int slot, int t) const {
+    const uint64_t g = reinterpret_cast<uint64_t>(P.grad) + elem_off(t);
+    const uint64_t gend = g + gbytes;
+    uint64_t g0 = (g + 15) & ~uint64_t(15), g1 = gend & ~uint64_t(15);
+    const unsigned char* src = slab(slot) + (g & 15);  // shared-memory image of byte g
+    if (g1 > g0) {
+      bulk_s2g(g0, smem_u32(src + (g0 - g)), (uint32_t)(g1 - g0));
+    } else {
+      g0 = gend; g1 = gend;  // everything by hand
     }
+    for (uint64_t q = g; q < g0; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
+    for (uint64_t q = g1; q < gend; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
+    bulk_commit();
   }
 
   __device__ __forceinline__ float group_max(float v) const {
@@ -472,221 +500,146 @@ struct Rows {
     return v;
   }
 
-  __device__ __forceinline__ void seg_max_sum(const float4 (&v)[CPL], float& m_run, float& s_run) const {
-    float m = m_run;
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) m = fmaxf(m, fmaxf(fmaxf(v[c].x, v[c].y), fmaxf(v[c].z, v[c].w)));
-    if (m > kNegInf) {
-      const float mb = m * kLog2e;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        s0 += ex2f(fmaf(v[c].x, kLog2e, -mb));
-        s1 += ex2f(fmaf(v[c].y, kLog2e, -mb));
-        s2 += ex2f(fmaf(v[c].z, kLog2e, -mb));
-        s3 += ex2f(fmaf(v[c].w, kLog2e, -mb));
-      }
-      s_run = (m_run > kNegInf ? s_run * ex2f((m_run - m) * kLog2e) : 0.f) + ((s0 + s1) + (s2 + s3));
-      m_run = m;
+  // chunk q of the row -> registers, floats of neighbouring rows (and chunks beyond the row) as -inf
+  __device__ __forceinline__ float4 load_chunk(const RowGeom& g, int q) const {
+    float4 v = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+    if (q < g.nch) {
+      v = g.srow[q];
+      if (q == 0) mask_head(v, g.off4);
+      if (q == g.nch - 1) mask_tail(v, g.rem);
+    }
+    return v;
+  }
+  // chunk q of the row <- y; only this row's floats of a boundary chunk
+  __device__ __forceinline__ void store_chunk(const RowGeom& g, int q, const float4& y) const {
+    if (q < g.nch) {
+      const int lo = q == 0 ? g.off4 : 0, hi = q == g.nch - 1 ? g.rem : 4;
+      if (lo == 0 && hi == 4) g.srow[q] = y;
+      else store_part(g.srow + q, y, lo, hi);
     }
   }
 
-  // emissions p_t(s) = softmax(x_t)[label_s] (gathered from the row's shared-memory copy) -> p-tile row
-  __device__ __forceinline__ void emit_row(const RowGeom& g, bool act, float lse, float* prow) const {
-    if (act) {
-      const float* xr = reinterpret_cast<const float*>(g.srow) + g.off4;
-      const float lb2 = lse * kLog2e;
-      float xv[NSL];
-#pragma unroll
-      for (int j = 0; j < NSL; ++j) {
-        const int l = label(j);
-        xv[j] = xr[l >= 0 ? (l & kLabMask) : 0];
-      }
-#pragma unroll
-      for (int j = 0; j < NSL; ++j) {
-        const float pv = label(j) >= 0 ? fmaxf(ex2f(fmaf(xv[j], kLog2e, -lb2)), kPMin) : 0.f;
-        prow[li + j * LPR] = pv;
-      }
-    }
-  }
+  // emissions p_t(s) = softmax(x_t)[label_s] = y[label_s] / w from the finished row (shared memory in phase 1,
+  // the gradient tensor in phase 2: the same float either way) -> p-tile row
+  __device__ __forceinline__ float emission(float y, int l) const { return l >= 0 ? fmaxf(y * winv, kPMin) : 0.f; }
 
-  // ---------------------------------------------------------------- phase 1: row log-partition + emissions
-  // tsl: this warp's time step slab of the tile; pt: p-tile of the item ([GB][PSEQ])
+  // ---------------------------------------------------------------- phase 1: one slab
+  // row log-partition, slab -> w*softmax in place (zeros beyond input_length), emissions
   __device__ __forceinline__ void forward_step(int t, unsigned char* tsl, float* pt) const {
     const bool act = t < Tb;  // Tb = 0 for sequences outside the group / the parity domain
     const RowGeom g = geom(t, tsl);
-    float m_run = kNegInf, s_run = 0.f;
     if (cfg.NSEG == 1) {
       float4 v[CPL];
-      load_seg(g, act, 0, v);
-      mask_seg<true>(g, 0, true, true, v);
-      seg_max_sum(v, m_run, s_run);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) v[c] = load_chunk(g, li + c * LPR);
+      float m_l = kNegInf;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) m_l = fmaxf(m_l, fmaxf(fmaxf(v[c].x, v[c].y), fmaxf(v[c].z, v[c].w)));
+      const float mb = (m_l > kNegInf) ? m_l * kLog2e : 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        v[c].x = ex2f(fmaf(v[c].x, kLog2e, -mb)); s0 += v[c].x;
+        v[c].y = ex2f(fmaf(v[c].y, kLog2e, -mb)); s1 += v[c].y;
+        v[c].z = ex2f(fmaf(v[c].z, kLog2e, -mb)); s2 += v[c].z;
+        v[c].w = ex2f(fmaf(v[c].w, kLog2e, -mb)); s3 += v[c].w;
+      }
+      const float m = group_max(m_l);
+      const float cf = (m_l > kNegInf) ? ex2f((m_l - m) * kLog2e) : 0.f;  // this lane's exponentials -> row maximum
+      const float s = group_sum(((s0 + s1) + (s2 + s3)) * cf);
+      const float sc = act ? weff * cf / s : 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) store_chunk(g, li + c * LPR, scale4(v[c], sc));
     } else {
+      // long rows: online max/sum over the segments, then a second pass over the slab
+      float m_l = kNegInf, s_l = 0.f;
       for (int seg = 0; seg < cfg.NSEG; ++seg) {
         float4 v[CPL];
-        load_seg(g, act, seg, v);
-        mask_seg<false>(g, seg, seg == 0, seg == cfg.NSEG - 1, v);
-        seg_max_sum(v, m_run, s_run);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) v[c] = load_chunk(g, seg * SEG + li + c * LPR);
+        float mm = m_l;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) mm = fmaxf(mm, fmaxf(fmaxf(v[c].x, v[c].y), fmaxf(v[c].z, v[c].w)));
+        if (mm > kNegInf) {
+          const float mb = mm * kLog2e;
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c)
+            s += (ex2f(fmaf(v[c].x, kLog2e, -mb)) + ex2f(fmaf(v[c].y, kLog2e, -mb))) +
+                 (ex2f(fmaf(v[c].z, kLog2e, -mb)) + ex2f(fmaf(v[c].w, kLog2e, -mb)));
+          s_l = (m_l > kNegInf ? s_l * ex2f((m_l - mm) * kLog2e) : 0.f) + s;
+          m_l = mm;
+        }
       }
-    }
-    const float m = group_max(m_run);
-    const float s = group_sum(m_run > kNegInf ? s_run * ex2f((m_run - m) * kLog2e) : 0.f);
-    const float lse = m + logf(s);
-    if (act && li == 0) lse_seq[t] = lse;
-    emit_row(g, act, lse, pt + seq * G::PSEQ + ti * PS);
-  }
-
-  // ---------------------------------------------------------------- phase 2 ahead stage: emissions again
-  __device__ __forceinline__ void emit_step(int t, unsigned char* tsl, float* pt) const {
-    const bool act = t < Tb;
-    const RowGeom g = geom(t, tsl);
-    emit_row(g, act, act ? lse_seq[t] : 0.f, pt + seq * G::PSEQ + ti * PS);
-  }
-
-  // w * softmax element; rc = (lse*log2e, w) of the element's row.  w = 0 (row beyond input_length, or stale
-  // ring contents that were never loaded) gives an exact 0 whatever x holds
-  static __device__ __forceinline__ float soft1(float x, float2 rc) {
-    return rc.y != 0.f ? rc.y * ex2f(fmaf(x, kLog2e, -rc.x)) : 0.f;
-  }
-
-  // ---------------------------------------------------------------- phase 2 behind stage: gradient rows
-  // The whole slab (GB rows, contiguous) becomes w*softmax(x) in place in the ring slot, chunk by chunk with
-  // the row constants of the (at most two) rows a chunk touches: zeros beyond input_length.
-  // Then -w*gamma is scattered onto each lane group's row; the producer warp streams the slab out with one
-  // TMA bulk store.  abt: alpha/beta tiles of the item ([GB][ABSEQ]); s2v: per-sequence gamma scale.
-  __device__ __forceinline__ void grad_step(int t, unsigned char* tsl, const double* abt, const double* s2v) const {
-    // row constants of the slab -> per-warp table (entry GB = "no row": exp2(-inf) = 0)
-    if (lane <= GB) {
-      const bool live_r = lane < GB && t < info[lane];
-      const float w_r = live_r ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + lane] : 1.f) : 0.f;
-      const float* lse_r = cfg.lse_global ? cfg.ws_lse + (size_t)min(b0 + lane, P.B - 1) * P.T : lse_seq + (lane - seq) * cfg.Tpad;
-      tab[lane] = make_float2(live_r ? lse_r[t] * kLog2e : INFINITY, w_r);
-    }
-    __syncwarp();
-    const int ph = slab_phase(t);
-    const int nchs = (ph + gcnt * C + 3) >> 2;  // chunks of the slab
-    float4* slab4 = reinterpret_cast<float4*>(tsl);
-    for (int seg = 0; seg < cfg.NSEG; ++seg) {
-      float4 v[CPL];
+      const float m = group_max(m_l);
+      const float s = group_sum(m_l > kNegInf ? s_l * ex2f((m_l - m) * kLog2e) : 0.f);
+      const float mb = m * kLog2e;
+      const float sc = act ? weff / s : 0.f;
+      for (int seg = 0; seg < cfg.NSEG; ++seg) {
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const int q = (seg * CPL + c) * 32 + lane;
-        if (q < nchs) v[c] = slab4[q];
-      }
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const int q = (seg * CPL + c) * 32 + lane;
-        if (q < nchs) {
-          const int e = 4 * q - ph;  // slab element index of the chunk's first float (head chunk: may be < 0)
-          int rA = 0;
-#pragma unroll
-          for (int r = 1; r < GB; ++r) rA += (e >= r * C) ? 1 : 0;
-          const int us = (rA + 1) * C - e;  // floats u >= us of the chunk belong to row rA+1
-          const float2 tA = tab[rA], tB = tab[rA + 1];
-          float4 x = v[c];
-          x.x = soft1(x.x, us > 0 ? tA : tB);
-          x.y = soft1(x.y, us > 1 ? tA : tB);
-          x.z = soft1(x.z, us > 2 ? tA : tB);
-          x.w = soft1(x.w, us > 3 ? tA : tB);
-          slab4[q] = x;
+        for (int c = 0; c < CPL; ++c) {
+          const int q = seg * SEG + li + c * LPR;
+          float4 v = load_chunk(g, q);
+          v.x = ex2f(fmaf(v.x, kLog2e, -mb)); v.y = ex2f(fmaf(v.y, kLog2e, -mb));
+          v.z = ex2f(fmaf(v.z, kLog2e, -mb)); v.w = ex2f(fmaf(v.w, kLog2e, -mb));
+          store_chunk(g, q, scale4(v, sc));
         }
       }
     }
     __syncwarp();
-    // gamma scatter: states that share a class are spread over rounds by their duplicate rank, so every round
-    // is a conflict-free read-add-write on the row (repeated labels accumulate, quirk 6)
-    const bool live = t < Tb;
-    const RowGeom g = geom(t, tsl);
-    float* xr = reinterpret_cast<float*>(g.srow) + g.off4;
-    float gam[NSL];
-    if (live) {
+    if (act) {
+      const float* yr = reinterpret_cast<const float*>(g.srow) + g.off4;
+      float* prow = pt + seq * G::PSEQ + ti * PS;
+      float yv[NSL];
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) {
+        const int l = label(j);
+        yv[j] = yr[l >= 0 ? l : 0];
+      }
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) prow[li + j * LPR] = emission(yv[j], label(j));
+    }
+  }
+
+  // ---------------------------------------------------------------- phase 2 ahead: emissions from the gradient rows
+  __device__ __forceinline__ void gather_issue(int t, float (&yv)[NSL]) const {
+    if (t >= 0 && t < Tb) {
+      const float* yr = P.grad + ((int64_t)t * P.B + b0 + seq) * C;
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) {
+        const int l = label(j);
+        yv[j] = __ldcg(yr + (l >= 0 ? l : 0));
+      }
+    }
+  }
+  __device__ __forceinline__ void gather_commit(int t, const float (&yv)[NSL], float* pt) const {
+    if (t >= 0 && t < Tb) {
+      float* prow = pt + seq * G::PSEQ + ti * PS;
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) prow[li + j * LPR] = emission(yv[j], label(j));
+    }
+  }
+
+  // ---------------------------------------------------------------- phase 2 behind: gamma scatter
+  // abt: alpha/beta tiles of the item ([GB][ABSEQ]); s2v: per-sequence gamma scale (-w/Z and the tile exponents)
+  __device__ __forceinline__ void scatter_step(int t, const double* abt, const double* s2v) const {
+    if (t < Tb && wgt != 0.f) {
       const double* at = abt + seq * G::ABSEQ + ti * AS;
       const double* bt = at + TT * AS;
       const double s2 = s2v[seq];
+      float* yr = P.grad + ((int64_t)t * P.B + b0 + seq) * C;
+      float gam[NSL];
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int st = li + j * LPR;
         gam[j] = label(j) >= 0 ? (float)(at[st] * (bt[st] * s2)) : 0.f;
       }
-    }
-    const int nr = __reduce_max_sync(0xffffffffu, live ? max_rank : 0);
-    for (int r = 0; r <= nr; ++r) {
-      if (live) {
 #pragma unroll
-        for (int j = 0; j < NSL; ++j) {
-          const int l = label(j);
-          if (l >= 0 && (l >> kLabBits) == r) xr[l & kLabMask] += gam[j];
-        }
-      }
-      if (r < nr) __syncwarp();
-    }
-  }
-};
-
-// ============================================================================ producer warp (TMA)
-// lane i moves time step i of a tile
-template <int TT>
-struct Producer {
-  const Problem& P;
-  const StreamCfg& cfg;
-  const Smem& S;
-  const int lane;
-  const int64_t b0;
-  const uint32_t gbytes;  // bytes of the group's rows at one time step
-  const uint64_t pol_keep;
-  const uint64_t lim;     // one past the last logit
-
-  __device__ __forceinline__ Producer(const Problem& P_, const StreamCfg& cfg_, const Smem& S_, int lane_, int64_t b0_, int gcnt)
-      : P(P_), cfg(cfg_), S(S_), lane(lane_), b0(b0_), gbytes((uint32_t)gcnt * (uint32_t)P_.C * 4u),
-        pol_keep(policy_evict_last()), lim(reinterpret_cast<uint64_t>(P_.logits) + (uint64_t)P_.T * P_.B * P_.C * 4u) {}
-
-  __device__ __forceinline__ uint64_t elem_off(int t) const { return (((uint64_t)t * P.B + b0) * P.C) * 4u; }
-
-  // rows of tile k, time steps [k*TT, k*TT+nvl) -> ring slot; 16-byte aligned superset of each time step's rows
-  __device__ __forceinline__ void load_item(int slot, int k, int nvl, bool keep) const {
-    uint64_t* bar = &S.sfull[slot];
-    if (lane < nvl) {
-      unsigned char* dst = S.ring + ((size_t)slot * TT + lane) * cfg.RSg;
-      const uint64_t a = reinterpret_cast<uint64_t>(P.logits) + elem_off(k * TT + lane);
-      const uint64_t a0 = a & ~uint64_t(15);
-      uint64_t a1 = (a + gbytes + 15) & ~uint64_t(15);
-      if (a1 > lim) {
-        // the tensor's last rows end inside a 16-byte chunk: the bulk copy stops before it, the rest goes by hand
-        a1 = lim & ~uint64_t(15);
-        const float* src = reinterpret_cast<const float*>(a1);
-        float* d = reinterpret_cast<float*>(dst + (a1 - a0));
-        const int n = (int)((a + gbytes - a1) >> 2);
-        for (int c = 0; c < n; ++c) d[c] = __ldg(src + c);
-      }
-      if (a1 > a0) {
-        const uint32_t nb = (uint32_t)(a1 - a0);
-        mbar_expect_tx(bar, nb);
-        if (keep) bulk_g2s_hint(smem_u32(dst), a0, nb, smem_u32(bar), pol_keep);
-        else bulk_g2s(smem_u32(dst), a0, nb, smem_u32(bar));
+      for (int j = 0; j < NSL; ++j) {
+        const int l = label(j);
+        if (l >= 0) atomicAdd(yr + l, gam[j]);
       }
     }
-    __syncwarp();  // every lane's expect_tx (and hand-copied tail) precedes the one arrival that can end the phase
-    if (lane == 0) mbar_arrive(bar);
-  }
-
-  // gradient rows of tile k, time steps [k*TT, k*TT+nvs): ring slot -> grad; the 16-byte aligned interior of
-  // each time step goes out as one bulk store, at most 3 floats on either side by hand.  Every lane commits one
-  // (possibly empty) bulk group per call, so that wait_group counts line up across lanes.
-  __device__ __forceinline__ void store_item(int slot, int k, int nvs) const {
-    if (lane < nvs) {
-      const uint64_t g = reinterpret_cast<uint64_t>(P.grad) + elem_off(k * TT + lane);
-      const uint64_t gend = g + gbytes;
-      uint64_t g0 = (g + 15) & ~uint64_t(15), g1 = gend & ~uint64_t(15);
-      const unsigned char* src = S.ring + ((size_t)slot * TT + lane) * cfg.RSg + (g & 15);  // image of byte g
-      if (g1 > g0) {
-        bulk_s2g(g0, smem_u32(src + (g0 - g)), (uint32_t)(g1 - g0));
-      } else {
-        g0 = gend; g1 = gend;  // everything by hand
-      }
-      for (uint64_t q = g; q < g0; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
-      for (uint64_t q = g1; q < gend; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
-    }
-    bulk_commit();
   }
 };
 
@@ -694,28 +647,26 @@ struct Producer {
 template <int NS, int LPR, int CPL, int MINB>
 __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_kernel(const Problem P, const StreamCfg cfg) {
   using G = Geo<NS, LPR>;
-  constexpr int TT = G::TT, Lpad = G::Lpad, PS = G::PS, AS = G::AS, GB = G::GB, NRW = G::NRW, NSLOT = kNSlot;
+  constexpr int TT = G::TT, Lpad = G::Lpad, PS = G::PS, AS = G::AS, GB = G::GB, NSL = G::NSL, NSLOT = kNSlot;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem S;
   S.sfull = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar);
   S.info = reinterpret_cast<int*>(smem_raw + cfg.o_info);
   S.lab = reinterpret_cast<int*>(smem_raw + cfg.o_lab);
-  S.lse = reinterpret_cast<float*>(smem_raw + cfg.o_lse);
   S.ckpt = reinterpret_cast<double*>(smem_raw + cfg.o_ckpt);
   S.cke = reinterpret_cast<int*>(smem_raw + cfg.o_cke);
   S.ptile = reinterpret_cast<float*>(smem_raw + cfg.o_ptile);
-  S.ab = reinterpret_cast<double*>(smem_raw + cfg.o_ab);
   S.s2 = reinterpret_cast<double*>(smem_raw + cfg.o_s2);
-  S.tab = reinterpret_cast<float2*>(smem_raw + cfg.o_tab);
   S.ring = smem_raw + cfg.o_ring;
+  S.ab = reinterpret_cast<double*>(smem_raw + cfg.o_ring);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * GB;
   const int gcnt = (int)min((int64_t)GB, P.B - b0);
 
   // ---- per-sequence lengths, labels, validity (include/nbctc.h parity domain)
-  if (tid < 2 * kMaxGB) S.info[2 * kMaxGB + tid] = 0;
-  if (tid < NSLOT) mbar_init(&S.sfull[tid], 1);
+  if (tid < kMaxGB) S.info[2 * kMaxGB + tid] = 0;
+  if (tid < NSLOT * TT) mbar_init(&S.sfull[tid], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -746,47 +697,33 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     S.info[kMaxGB + tid] = Lb;
   }
   __syncthreads();
-  // duplicate ranks (the loop reads the class bits of earlier states while later ones may already be packed)
-  for (int idx = tid; idx < GB * Lpad; idx += G::NTHREADS) {
-    const int r = idx / Lpad, s = idx - r * Lpad;
-    int rank = 0;
-    if (s < S.info[kMaxGB + r]) {
-      const int l = S.lab[idx] & kLabMask;
-      for (int q = 0; q < s; ++q) rank += ((S.lab[r * Lpad + q] & kLabMask) == l) ? 1 : 0;
-      if (rank > 0) {
-        atomicMax(&S.info[3 * kMaxGB + r], rank);
-        S.lab[idx] = l | (rank << kLabBits);
-      }
-    }
-  }
-  __syncthreads();
   int Tg = 0;
 #pragma unroll
   for (int r = 0; r < GB; ++r) Tg = max(Tg, S.info[r]);
   const int NTg = (Tg + TT - 1) / TT;
   const bool want_grad = P.grad != nullptr;
-  const int total = want_grad ? 2 * NTg : NTg;
-  const size_t slot_bytes = (size_t)TT * cfg.RSg;
   PROF_DECL
 
   // rows beyond the group's longest input: all-zero gradient, written directly (only ragged batches get here)
-  if (want_grad && NTg * TT < P.T) {
+  if (want_grad && Tg < P.T) {
     const int64_t n = (int64_t)gcnt * P.C;
-    for (int64_t t = (int64_t)NTg * TT; t < P.T; ++t) {
+    for (int64_t t = Tg; t < P.T; ++t) {
       float* dst = P.grad + (t * P.B + b0) * P.C;
       for (int64_t c = tid; c < n; c += G::NTHREADS) dst[c] = 0.f;
     }
   }
 
 #ifdef NBCTC_PROF
+  int prof_it_ = 0;
 #define NBCTC_ITER_END()                                                                            \
   {                                                                                                 \
     const long long t_work_ = clock64();                                                            \
     PROF_SCOPE(6, __syncthreads(); prof_[5] += *reinterpret_cast<volatile int*>(S.info) & 0)         \
-    if (cfg.prof != nullptr && blockIdx.x == gridDim.x / 2 && lane == 0 && it + 1 < 128) {           \
-      cfg.prof[24 + ((it + 1) * 32 + warp) * 2] = t_work_ - prof_t0_;                                \
-      cfg.prof[24 + ((it + 1) * 32 + warp) * 2 + 1] = clock64() - prof_t0_;                          \
+    if (cfg.prof != nullptr && blockIdx.x == gridDim.x / 2 && lane == 0 && prof_it_ < 160) {         \
+      cfg.prof[24 + (prof_it_ * 32 + warp) * 2] = t_work_ - prof_t0_;                                \
+      cfg.prof[24 + (prof_it_ * 32 + warp) * 2 + 1] = clock64() - prof_t0_;                          \
     }                                                                                               \
+    ++prof_it_;                                                                                     \
   }
 #else
 #define NBCTC_ITER_END() __syncthreads();
@@ -808,90 +745,134 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     chain.carry = (lane == 0) ? 1.0 : 0.0;
     chain.zinv = 0.0;
     chain.Ea = 0; chain.Eb = 0; chain.Ez = 0;
-    for (int it = -1; it <= total + 1; ++it) {
-      if (it >= 0 && it < total) {
-        const int buf = it & 1;
-        const float* pt = S.ptile + (size_t)(buf * GB + seq) * G::PSEQ;
-        if (it < NTg) {
-          if (it < NTb) {
-            PROF_SCOPE(0, chain_phase1<NS, TT, PS>(cx, chain, lane, Tb, ck, cke, it, pt))
-            if (it == NTb - 1) chain_readout<NS>(cx, chain, lane, Lb, &P.loss[b0 + seq], wgt);
-          }
-        } else {
-          const int k = 2 * NTg - 1 - it;
-          if (k < NTb) {
-            PROF_SCOPE(1, chain_phase2<NS, TT, PS, AS>(cx, chain, lane, Tb, ck, cke, k, pt,
-                                                       S.ab + (size_t)(buf * GB + seq) * G::ABSEQ, &S.s2[buf * GB + seq]))
-          }
-        }
+    // ---- phase 1
+    for (int it = -1; it < NTg; ++it) {
+      if (it >= 0 && it < NTb) {
+        const float* pt = S.ptile + (size_t)((it & 1) * GB + seq) * G::PSEQ;
+        PROF_SCOPE(0, chain_phase1<NS, TT, PS>(cx, chain, lane, Tb, ck, cke, it, pt))
+        // the gradient weight of a sequence with w = 0 is applied at the end of the kernel (see below)
+        if (it == NTb - 1) chain_readout<NS>(cx, chain, lane, Lb, &P.loss[b0 + seq], wgt);
       }
       NBCTC_ITER_END()
+    }
+    // ---- phase 2: item i = tile NTg-1-i
+    if (want_grad) {
+      double ckv[NS];
+      int EaK = 0;
+      auto fetch_ckpt = [&](int k) {  // checkpoint of tile k (k = 0 starts from the virtual state instead)
+        if (k > 0 && k < NTb) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) ckv[j] = ck[(k * NS + j) * 16];
+          EaK = cke[k];
+        } else {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) ckv[j] = 0.0;
+          EaK = 0;
+        }
+      };
+      fetch_ckpt(NTg - 1);
+      for (int i = -1; i <= NTg; ++i) {
+        if (i >= 0 && i < NTg) {
+          const int k = NTg - 1 - i;
+          if (k < NTb) {
+            double ckc[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) ckc[j] = ckv[j];
+            const int EaC = EaK;
+            fetch_ckpt(k - 1);  // in flight while this tile runs
+            const int buf = i & 1;
+            PROF_SCOPE(1, chain_phase2<NS, TT, PS, AS>(cx, chain, lane, Tb, ckc, EaC, k,
+                                                       S.ptile + (size_t)(buf * GB + seq) * G::PSEQ,
+                                                       S.ab + (size_t)(buf * GB + seq) * G::ABSEQ, &S.s2[buf * GB + seq]))
+          } else {
+            fetch_ckpt(k - 1);
+          }
+        }
+        NBCTC_ITER_END()
+      }
     }
     PROF_DUMP(0)
-  } else if (warp < GB + NRW) {
+  } else {
     // ======================================================================== row warp of time step `ti`
     const int ti = warp - GB;
-    const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0);
-    for (int it = -1; it <= total + 1; ++it) {
-      const int a = it + 1;  // ahead item
-      if (a >= 0 && a < total) {
-        const int slot = a % NSLOT;
-        PROF_SCOPE(0, mbar_wait(&S.sfull[slot], (uint32_t)(a / NSLOT) & 1u))
-        float* pt = S.ptile + (size_t)((a & 1) * GB) * G::PSEQ;
-        unsigned char* tsl = S.ring + slot * slot_bytes + (size_t)ti * cfg.RSg;
-        if (a < NTg) {
-          PROF_SCOPE(1, rows.forward_step(a * TT + ti, tsl, pt))
-        } else {
-          PROF_SCOPE(2, rows.emit_step((2 * NTg - 1 - a) * TT + ti, tsl, pt))
+    const int seq = lane / LPR;
+    const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
+    const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
+    // ---- phase 1: item a = tile a, this warp's time step t = a*TT + ti (only t < Tg is ever moved)
+    if (lane == 0) {
+      for (int a = 0; a < 2; ++a)
+        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti);
+    }
+    for (int it = -1; it < NTg; ++it) {
+      const int a = it + 1;
+      if (a < NTg) {
+        const int t = a * TT + ti;
+        if (lane == 0 && (a + 2) * TT + ti < Tg) {
+          // slot of item a+2 was last used by item a-2, whose store was committed two iterations ago
+          if (want_grad) PROF_SCOPE(2, bulk_wait_read<1>())
+          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti))
         }
-      }
-      const int g = it - 1;  // behind item
-      if (g >= NTg && g < total) {
-        const int t = (2 * NTg - 1 - g) * TT + ti;
-        if (t < P.T) {
-          const int buf = g & 1;
-          PROF_SCOPE(3, rows.grad_step(t, S.ring + (g % NSLOT) * slot_bytes + (size_t)ti * cfg.RSg,
-                                       S.ab + (size_t)(buf * GB) * G::ABSEQ, S.s2 + buf * GB))
+        if (t < Tg) {
+          const int slot = a % NSLOT;
+          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (uint32_t)(a / NSLOT) & 1u))
+          PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
+          if (want_grad) {
+            fence_proxy_async();  // the slab is read by the async proxy (bulk store) next
+            __syncwarp();
+            if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t))
+          }
         }
-        fence_proxy_async();  // the slot is read by the async proxy (bulk store) after the barrier
       }
       NBCTC_ITER_END()
+    }
+    if (want_grad) {
+      // every gradient row of phase 1 is in global memory before phase 2 reads it (and the ring becomes the
+      // alpha/beta tiles)
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
+      // ---- phase 2: item i = tile NTg-1-i
+      float yv[NSL];
+      rows.gather_issue((NTg - 1) * TT + ti, yv);
+      for (int i = -1; i <= NTg; ++i) {
+        const int ia = i + 1;  // ahead item: emissions
+        if (ia < NTg) {
+          const int t = (NTg - 1 - ia) * TT + ti;
+          PROF_SCOPE(4, rows.gather_commit(t, yv, S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
+          rows.gather_issue(t - TT, yv);  // next item's rows: in flight until the next iteration
+        }
+        const int ib = i - 1;  // behind item: gamma scatter
+        if (ib >= 0) {
+          const int t = (NTg - 1 - ib) * TT + ti;
+          PROF_SCOPE(5, rows.scatter_step(t, S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
+        }
+        NBCTC_ITER_END()
+      }
     }
     PROF_DUMP(1)
-  } else {
-    // ======================================================================== producer warp
-    const Producer<TT> prod(P, cfg, S, lane, b0, gcnt);
-    int next_load = 0;
-    for (int it = -1; it <= total + 1; ++it) {
-      const int s = it - 2;  // item whose gradient rows are complete
-      if (s >= NTg && s < total) {
-        const int k = 2 * NTg - 1 - s;
-        PROF_SCOPE(0, prod.store_item(s % NSLOT, k, min(TT, (int)P.T - k * TT)))
-      }
-      while (next_load < total && next_load <= it + NSLOT) {
-        const int occ = next_load - NSLOT;  // previous occupant of the slot
-        if (occ >= 0) {
-          const int free_at = occ < NTg ? occ : occ + 3;
-          if (free_at > it) break;
-          if (occ >= NTg) PROF_SCOPE(1, bulk_wait_read<1>())  // all but the store committed just above have been read
-        }
-        const int k = next_load < NTg ? next_load : 2 * NTg - 1 - next_load;
-        PROF_SCOPE(2, prod.load_item(next_load % NSLOT, k, min(TT, Tg - k * TT), next_load < NTg))
-        ++next_load;
-      }
-      NBCTC_ITER_END()
-    }
-    bulk_wait_read<0>();  // the ring must outlive the last bulk store's reads
-    PROF_DUMP(2)
   }
 #undef NBCTC_ITER_END
+
+  // Sequences with gradient weight 0 ran with weight 1 (their emissions are read back from the gradient rows):
+  // their rows become zeros now.  (Their gamma scatter was skipped.)
+  if (want_grad) {
+    for (int r = 0; r < gcnt; ++r) {
+      const float w_r = P.w_scalar * (P.seq_w ? P.seq_w[b0 + r] : 1.f);
+      const int Tr = S.info[r];
+      if (w_r == 0.f && Tr > 0) {
+        for (int t = 0; t < Tr; ++t) {
+          float* dst = P.grad + ((int64_t)t * P.B + b0 + r) * P.C;
+          for (int c = tid; c < P.C; c += G::NTHREADS) dst[c] = 0.f;
+        }
+      }
+    }
+  }
 }
 
 template <int NS, int LPR, int CPL>
 int launch_inst(const Problem& p, const StreamCfg& cfg, cudaStream_t stream) {
   using G = Geo<NS, LPR>;
   const unsigned groups = (unsigned)((p.B + G::GB - 1) / G::GB);
-  if constexpr (G::GB <= 2) {
+  if constexpr (G::NTHREADS * 2 <= 1024) {
     if (cfg.ctas_per_sm >= 2) {
       auto kern = nbctc_stream_kernel<NS, LPR, CPL, 2>;
       if (cfg.smem_bytes > 48 * 1024)

@@ -26,7 +26,7 @@ x = torch.randn((T, B, Cc), device=dev)
 tgt, ilt, tlt = torch.tensor(tg, device=dev), torch.tensor(il, device=dev), torch.tensor(tl, device=dev)
 lib = _ffi.lib()
 lib.nbctc_debug_set_prof.argtypes = [C.c_void_p]
-prof = torch.zeros(24 + 128 * 32 * 2, dtype=torch.int64, device=dev)
+prof = torch.zeros(24 + 160 * 32 * 2, dtype=torch.int64, device=dev)
 per = torch.empty(B, device=dev)
 grad = torch.empty_like(x)
 ws_bytes = int(lib.nbctc_workspace_bytes(T, B, Cc, Lmax, 0, 0))
@@ -49,12 +49,11 @@ e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 pall = prof.cpu().numpy().astype(np.float64)
 p = pall[:24].reshape(3, 8)
-trace = pall[24:].reshape(128, 32, 2)
+trace = pall[24:].reshape(160, 32, 2)
 groups = (B + GB - 1) // GB
 names = {
     0: ("chain", GB, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
-    1: ("row", NRW, ["wait rows", "forward (LSE+emit)", "emit", "grad", "-", "-", "barrier", "total"]),
-    2: ("producer", 1, ["store issue", "wait store reads", "load issue", "-", "-", "-", "barrier", "total"]),
+    1: ("row", NRW, ["wait rows", "forward step", "wait store reads", "TMA issue", "gather commit", "scatter", "barrier", "total"]),
 }
 print(f"workload {name}: GB={GB} NRW={NRW} groups={groups} kernel {e0.elapsed_time(e1):.3f} ms (instrumented); "
       f"mean cycles per warp per CTA")
@@ -63,13 +62,13 @@ for role, (rn, nw, nm) in names.items():
     print(f"  {rn:9s} " + "  ".join(f"{n}={v:,.0f}" for n, v in zip(nm, m) if n != "-"))
 
 # per-iteration trace of the middle CTA: cycles each role spends working in the iteration (work end - previous barrier end)
-nw = GB + NRW + 1
+nw = GB + NRW
 prev = np.zeros(nw)
-print("trace of one CTA: it | iteration cycles | busy cycles chain(max) rows(max) producer")
-for itx in range(128):
+print("trace of one CTA: iteration | iteration cycles | busy cycles chain(max) rows(max)")
+for itx in range(160):
     if trace[itx, :nw, 1].max() == 0:
         break
     busy = trace[itx, :nw, 0] - prev
     end = trace[itx, :nw, 1]
-    print(f"  it={itx - 1:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f} prod={busy[GB + NRW]:6.0f}")
+    print(f"  it={itx:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f}")
     prev = end
