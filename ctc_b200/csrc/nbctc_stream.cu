@@ -80,15 +80,15 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
     c.ckpt_global = ck_glob;
     c.RSg = (int)align_up((size_t)gb * C * 4, 16) + 32;
     c.o_bar = take(sizeof(uint64_t) * kNSlot * c.TT);
-    c.o_info = take(sizeof(int) * 3 * kMaxGB);
+    c.o_info = take(sizeof(int) * 4 * kMaxGB);
     c.o_lab = take(sizeof(int) * gb * c.Lpad);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)gb * c.NTmax * c.Lpad);
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
     c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * PSEQ);
     c.o_s2 = take(sizeof(double) * 2 * gb);
+    c.o_ab = take(sizeof(double) * 2 * (size_t)gb * ABSEQ);
     off = align_up(off, 128);
-    // the ring (phase 1) and the alpha/beta tiles (phase 2) share one region
-    c.o_ring = take(std::max((size_t)kNSlot * c.TT * c.RSg, sizeof(double) * 2 * (size_t)gb * ABSEQ));
+    c.o_ring = take((size_t)kNSlot * c.TT * c.RSg);
     c.smem_bytes = (uint32_t)off;
     return off;
   };

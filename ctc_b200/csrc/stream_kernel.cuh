@@ -14,17 +14,17 @@
 //                              chain warps  item it: alpha over the tile (NoBlankCTC.py:71-87), 16 lanes x NS
 //                                           states in float64, linear domain, exact power-of-two rescaling and one
 //                                           checkpoint per tile
-//   phase 2 (tiles downwards)  row warps    item it+1: the same emissions again, gathered from the gradient rows
-//                                           written in phase 1 (L2 hits; bit-identical to phase 1);
-//                                           item it-1: gamma = alpha*beta/Z from the chain's tiles, -w*gamma added
-//                                           to the gradient rows with global float reductions (repeated labels
-//                                           accumulate)
+//   phase 2 (tiles downwards)  row warps    the finished slabs come back from the gradient tensor (L2 hits).  Item it+1:
+//                                           the same emissions again (bit-identical to phase 1); item it-1:
+//                                           gamma = alpha*beta/Z from the chain's tiles, -w*gamma added to the slab
+//                                           in shared memory (repeated labels accumulate), and
+//                                           the slab goes back with one bulk store
 //                              chain warps  item it: lanes 0-15 replay alpha inside the tile from the checkpoint
 //                                           while lanes 16-31 run beta in the same instructions (beta is kept in
 //                                           reversed state order)
 //
-// HBM traffic: the logits are read once, the gradient is written once; the phase-2 gathers / reductions touch
-// lines that were written a few microseconds earlier by the same SM.
+// HBM traffic: the logits are read once and the gradient is written once, as long as the gradient rows of the
+// sequences in flight stay in L2 between their two phases.
 // Template parameters: NS (chain states per lane, Lmax <= 16*NS), LPR (lanes per row; GB = 32/LPR sequences per
 // CTA), CPL (16-byte chunks per lane and row segment).
 #pragma once
@@ -36,7 +36,7 @@
 namespace nbctc {
 
 constexpr int kMaxGB = 8;   // sequences per group upper bound (LPR = 4)
-constexpr int kNSlot = 4;   // ring depth (tiles): two loading, one being worked on, one draining
+constexpr int kNSlot = 5;   // ring depth (tiles)
 
 struct StreamCfg {
   int NS, Lpad, TT;
@@ -46,7 +46,7 @@ struct StreamCfg {
   int NTmax;  // ceil(T / TT)
   int ckpt_global;
   int ctas_per_sm;
-  uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_ring, smem_bytes;
+  uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_ab, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
   int* ws_cke;      // [B][NTmax]
   long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [160][32][2] trace
@@ -77,6 +77,10 @@ namespace stream {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kPMin = 7.52316385e-37f;  // 2^-120: emission floor (8 steps stay inside the f64 range)
 constexpr float kNegInf = -INFINITY;
+// label slots in shared memory / registers: class index in the low 22 bits, above it the state's rank among the
+// earlier states with the same class (the gamma scatter runs one conflict-free round per rank); -1 = no state
+constexpr int kLabBits = 22;
+constexpr int kLabMask = (1 << kLabBits) - 1;
 
 // ---------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,14 +181,14 @@ __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the
 
 struct Smem {
   uint64_t* sfull;  // [kNSlot][TT] "this time step's slab has landed" barriers
-  int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags
+  int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags, [3*kMaxGB..) largest duplicate rank
   int* lab;         // [GB][Lpad]
   double* ckpt;     // [GB][NTmax][Lpad]   (or in the workspace)
   int* cke;         // [GB][NTmax]
   float* ptile;     // [2][GB][PSEQ]
   double* s2;       // [2][GB]
-  unsigned char* ring;  // [kNSlot][TT][RSg] in phase 1
-  double* ab;       // [2][GB][ABSEQ] in phase 2 (same memory as the ring)
+  double* ab;       // [2][GB][ABSEQ]
+  unsigned char* ring;  // [kNSlot][TT][RSg]
 };
 
 // ============================================================================ chain warp
@@ -404,7 +408,7 @@ struct Rows {
   const int ti;             // this warp's time step inside a tile
   const int gcnt;
   const int64_t b0;
-  const int Tb, Lb, C;
+  const int Tb, Lb, C, max_rank;
   const uint32_t gbytes;    // bytes of the group's rows at one time step
   const float wgt;          // gradient weight of the sequence; weff = wgt, or 1 where wgt == 0 (see kernel tail)
   const float weff, winv;
@@ -414,7 +418,7 @@ struct Rows {
   __device__ __forceinline__ Rows(const Problem& P_, const StreamCfg& cfg_, const Smem& S_, int lane_, int ti_, int gcnt_,
                                   int64_t b0_, float wgt_)
       : P(P_), cfg(cfg_), S(S_), lane(lane_), li(lane_ & (LPR - 1)), seq(lane_ / LPR), ti(ti_), gcnt(gcnt_), b0(b0_),
-        Tb(S_.info[lane_ / LPR]), Lb(S_.info[kMaxGB + lane_ / LPR]), C((int)P_.C),
+        Tb(S_.info[lane_ / LPR]), Lb(S_.info[kMaxGB + lane_ / LPR]), C((int)P_.C), max_rank(S_.info[3 * kMaxGB + lane_ / LPR]),
         gbytes((uint32_t)gcnt_ * (uint32_t)P_.C * 4u), wgt(wgt_), weff(wgt_ != 0.f ? wgt_ : 1.f),
         winv(1.f / (wgt_ != 0.f ? wgt_ : 1.f)), lab_seq(S_.lab + (lane_ / LPR) * Lpad) {
     if constexpr (kLabRegs) {
@@ -449,12 +453,12 @@ struct Rows {
   }
 
   // ---------------------------------------------------------------- TMA (lane 0 only)
-  // logits rows of time step t -> ring slot: 16-byte aligned superset of the slab
-  __device__ __forceinline__ void issue_load(int slot, int t) const {
+  // rows of time step t of `base` (logits, or the gradient in phase 2) -> ring slot: 16-byte aligned superset
+  __device__ __forceinline__ void issue_load(int slot, int t, const float* base) const {
     uint64_t* bar = &S.sfull[slot * TT + ti];
     unsigned char* dst = slab(slot);
-    const uint64_t a = reinterpret_cast<uint64_t>(P.logits) + elem_off(t);
-    const uint64_t lim = reinterpret_cast<uint64_t>(P.logits) + (uint64_t)P.T * P.B * P.C * 4u;
+    const uint64_t a = reinterpret_cast<uint64_t>(base) + elem_off(t);
+    const uint64_t lim = reinterpret_cast<uint64_t>(base) + (uint64_t)P.T * P.B * P.C * 4u;
     const uint64_t a0 = a & ~uint64_t(15);
     uint64_t a1 = (a + gbytes + 15) & ~uint64_t(15);
     if (a1 > lim) {
@@ -594,51 +598,59 @@ struct Rows {
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int l = label(j);
-        yv[j] = yr[l >= 0 ? l : 0];
+        yv[j] = yr[l >= 0 ? (l & kLabMask) : 0];
       }
 #pragma unroll
       for (int j = 0; j < NSL; ++j) prow[li + j * LPR] = emission(yv[j], label(j));
     }
   }
 
-  // ---------------------------------------------------------------- phase 2 ahead: emissions from the gradient rows
-  __device__ __forceinline__ void gather_issue(int t, float (&yv)[NSL]) const {
-    if (t >= 0 && t < Tb) {
-      const float* yr = P.grad + ((int64_t)t * P.B + b0 + seq) * C;
+  // ---------------------------------------------------------------- phase 2 ahead: emissions from the slab again
+  __device__ __forceinline__ void emit_step(int t, unsigned char* tsl, float* pt) const {
+    if (t < Tb) {
+      const RowGeom g = geom(t, tsl);
+      const float* yr = reinterpret_cast<const float*>(g.srow) + g.off4;
+      float* prow = pt + seq * G::PSEQ + ti * PS;
+      float yv[NSL];
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int l = label(j);
-        yv[j] = __ldcg(yr + (l >= 0 ? l : 0));
+        yv[j] = yr[l >= 0 ? (l & kLabMask) : 0];
       }
-    }
-  }
-  __device__ __forceinline__ void gather_commit(int t, const float (&yv)[NSL], float* pt) const {
-    if (t >= 0 && t < Tb) {
-      float* prow = pt + seq * G::PSEQ + ti * PS;
 #pragma unroll
       for (int j = 0; j < NSL; ++j) prow[li + j * LPR] = emission(yv[j], label(j));
     }
   }
 
-  // ---------------------------------------------------------------- phase 2 behind: gamma scatter
-  // abt: alpha/beta tiles of the item ([GB][ABSEQ]); s2v: per-sequence gamma scale (-w/Z and the tile exponents)
-  __device__ __forceinline__ void scatter_step(int t, const double* abt, const double* s2v) const {
-    if (t < Tb && wgt != 0.f) {
+  // ---------------------------------------------------------------- phase 2 behind: gamma scatter into the slab
+  // abt: alpha/beta tiles of the item ([GB][ABSEQ]); s2v: per-sequence gamma scale (-w/Z and the tile exponents).
+  // States that share a class are spread over rounds by their duplicate rank, so every round is a conflict-free
+  // read-add-write on the row.
+  __device__ __forceinline__ void scatter_step(int t, unsigned char* tsl, const double* abt, const double* s2v) const {
+    const bool live = t < Tb && wgt != 0.f;
+    const RowGeom g = geom(t, tsl);
+    float* yr = reinterpret_cast<float*>(g.srow) + g.off4;
+    float gam[NSL];
+    if (live) {
       const double* at = abt + seq * G::ABSEQ + ti * AS;
       const double* bt = at + TT * AS;
       const double s2 = s2v[seq];
-      float* yr = P.grad + ((int64_t)t * P.B + b0 + seq) * C;
-      float gam[NSL];
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int st = li + j * LPR;
         gam[j] = label(j) >= 0 ? (float)(at[st] * (bt[st] * s2)) : 0.f;
       }
+    }
+    const int nr = __reduce_max_sync(0xffffffffu, live ? max_rank : 0);
+    for (int r = 0; r <= nr; ++r) {
+      if (live) {
 #pragma unroll
-      for (int j = 0; j < NSL; ++j) {
-        const int l = label(j);
-        if (l >= 0) atomicAdd(yr + l, gam[j]);
+        for (int j = 0; j < NSL; ++j) {
+          const int l = label(j);
+          if (l >= 0 && (l >> kLabBits) == r) yr[l & kLabMask] += gam[j];
+        }
       }
+      if (r < nr) __syncwarp();
     }
   }
 };
@@ -657,16 +669,16 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
   S.cke = reinterpret_cast<int*>(smem_raw + cfg.o_cke);
   S.ptile = reinterpret_cast<float*>(smem_raw + cfg.o_ptile);
   S.s2 = reinterpret_cast<double*>(smem_raw + cfg.o_s2);
+  S.ab = reinterpret_cast<double*>(smem_raw + cfg.o_ab);
   S.ring = smem_raw + cfg.o_ring;
-  S.ab = reinterpret_cast<double*>(smem_raw + cfg.o_ring);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * GB;
   const int gcnt = (int)min((int64_t)GB, P.B - b0);
 
   // ---- per-sequence lengths, labels, validity (include/nbctc.h parity domain)
-  if (tid < kMaxGB) S.info[2 * kMaxGB + tid] = 0;
-  if (tid < NSLOT * TT) mbar_init(&S.sfull[tid], 1);
+  if (tid < 2 * kMaxGB) S.info[2 * kMaxGB + tid] = 0;
+  for (int i = tid; i < NSLOT * TT; i += G::NTHREADS) mbar_init(&S.sfull[i], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -695,6 +707,20 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     }
     S.info[tid] = Tb;
     S.info[kMaxGB + tid] = Lb;
+  }
+  __syncthreads();
+  // duplicate ranks (the loop reads the class bits of earlier states while later ones may already be packed)
+  for (int idx = tid; idx < GB * Lpad; idx += G::NTHREADS) {
+    const int r = idx / Lpad, s = idx - r * Lpad;
+    int rank = 0;
+    if (s < S.info[kMaxGB + r]) {
+      const int l = S.lab[idx] & kLabMask;
+      for (int q = 0; q < s; ++q) rank += ((S.lab[r * Lpad + q] & kLabMask) == l) ? 1 : 0;
+      if (rank > 0) {
+        atomicMax(&S.info[3 * kMaxGB + r], rank);
+        S.lab[idx] = l | (rank << kLabBits);
+      }
+    }
   }
   __syncthreads();
   int Tg = 0;
@@ -799,22 +825,25 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
     // ---- phase 1: item a = tile a, this warp's time step t = a*TT + ti (only t < Tg is ever moved)
+    uint32_t par = 0;  // bit s = parity of the next completion of this warp's barrier of slot s
+    int n = 0;         // items started by this warp (ring position), continues into phase 2
     if (lane == 0) {
       for (int a = 0; a < 2; ++a)
-        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti);
+        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti, P.logits);
     }
     for (int it = -1; it < NTg; ++it) {
       const int a = it + 1;
       if (a < NTg) {
         const int t = a * TT + ti;
         if (lane == 0 && (a + 2) * TT + ti < Tg) {
-          // slot of item a+2 was last used by item a-2, whose store was committed two iterations ago
+          // slot of item a+2 was last used by item a-3, whose store was committed three iterations ago
           if (want_grad) PROF_SCOPE(2, bulk_wait_read<1>())
-          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti))
+          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti, P.logits))
         }
         if (t < Tg) {
           const int slot = a % NSLOT;
-          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (uint32_t)(a / NSLOT) & 1u))
+          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
+          par ^= 1u << slot;
           PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
           if (want_grad) {
             fence_proxy_async();  // the slab is read by the async proxy (bulk store) next
@@ -825,28 +854,41 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
       }
       NBCTC_ITER_END()
     }
+    n = NTg;
     if (want_grad) {
-      // every gradient row of phase 1 is in global memory before phase 2 reads it (and the ring becomes the
-      // alpha/beta tiles)
+      // every gradient row of phase 1 is in global memory before phase 2 reads it back
       if (lane == 0) bulk_wait_all();
       __syncwarp();
-      // ---- phase 2: item i = tile NTg-1-i
-      float yv[NSL];
-      rows.gather_issue((NTg - 1) * TT + ti, yv);
+      // ---- phase 2: item i = tile NTg-1-i at ring position n + i; slabs come back from the gradient tensor
+      auto t_of = [&](int i) { return (NTg - 1 - i) * TT + ti; };
+      if (lane == 0) {
+        for (int i = 0; i < 2 && i < NTg; ++i)
+          if (t_of(i) < Tg) rows.issue_load((n + i) % NSLOT, t_of(i), P.grad);
+      }
       for (int i = -1; i <= NTg; ++i) {
-        const int ia = i + 1;  // ahead item: emissions
-        if (ia < NTg) {
-          const int t = (NTg - 1 - ia) * TT + ti;
-          PROF_SCOPE(4, rows.gather_commit(t, yv, S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
-          rows.gather_issue(t - TT, yv);  // next item's rows: in flight until the next iteration
+        if (lane == 0 && i >= 0 && i + 2 < NTg && t_of(i + 2) < Tg) {
+          // slot of item i+2 was last used by item i-3, whose store was committed two iterations ago
+          PROF_SCOPE(2, bulk_wait_read<1>())
+          PROF_SCOPE(3, rows.issue_load((n + i + 2) % NSLOT, t_of(i + 2), P.grad))
         }
-        const int ib = i - 1;  // behind item: gamma scatter
-        if (ib >= 0) {
-          const int t = (NTg - 1 - ib) * TT + ti;
-          PROF_SCOPE(5, rows.scatter_step(t, S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
+        const int ia = i + 1;  // ahead item: emissions
+        if (ia < NTg && t_of(ia) < Tg) {
+          const int slot = (n + ia) % NSLOT;
+          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
+          par ^= 1u << slot;
+          PROF_SCOPE(4, rows.emit_step(t_of(ia), rows.slab(slot), S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
+        }
+        const int ib = i - 1;  // behind item: gamma scatter, slab back to the gradient tensor
+        if (ib >= 0 && t_of(ib) < Tg) {
+          const int slot = (n + ib) % NSLOT;
+          PROF_SCOPE(5, rows.scatter_step(t_of(ib), rows.slab(slot), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t_of(ib)))
         }
         NBCTC_ITER_END()
       }
+      if (lane == 0) bulk_wait_all();  // the ring must outlive the last bulk store's reads; rows final before the tail
     }
     PROF_DUMP(1)
   }
@@ -854,6 +896,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
 
   // Sequences with gradient weight 0 ran with weight 1 (their emissions are read back from the gradient rows):
   // their rows become zeros now.  (Their gamma scatter was skipped.)
+  __syncthreads();
   if (want_grad) {
     for (int r = 0; r < gcnt; ++r) {
       const float w_r = P.w_scalar * (P.seq_w ? P.seq_w[b0 + r] : 1.f);
