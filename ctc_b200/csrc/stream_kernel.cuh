@@ -133,14 +133,15 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, uint64_t src_gm
       "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, uint64_t src_gmem, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src_gmem), "r"(bytes), "r"(bar)
+__device__ __forceinline__ void bulk_s2g_hint(uint64_t dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(uint64_t dst_gmem, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
-               : "memory");
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -454,7 +455,7 @@ struct Rows {
 
   // ---------------------------------------------------------------- TMA (lane 0 only)
   // rows of time step t of `base` (logits, or the gradient in phase 2) -> ring slot: 16-byte aligned superset
-  __device__ __forceinline__ void issue_load(int slot, int t, const float* base) const {
+  __device__ __forceinline__ void issue_load(int slot, int t, const float* base, uint64_t pol) const {
     uint64_t* bar = &S.sfull[slot * TT + ti];
     unsigned char* dst = slab(slot);
     const uint64_t a = reinterpret_cast<uint64_t>(base) + elem_off(t);
@@ -470,7 +471,7 @@ struct Rows {
       for (int c = 0; c < n; ++c) d[c] = __ldg(src + c);
     }
     if (a1 > a0) {
-      bulk_g2s(smem_u32(dst), a0, (uint32_t)(a1 - a0), smem_u32(bar));
+      bulk_g2s_hint(smem_u32(dst), a0, (uint32_t)(a1 - a0), smem_u32(bar), pol);
       mbar_arrive_expect_tx(bar, (uint32_t)(a1 - a0));  // the phase cannot complete before this arrival
     } else {
       mbar_arrive(bar);
@@ -478,13 +479,13 @@ struct Rows {
   }
   // finished slab of time step t -> gradient rows: the 16-byte aligned interior as one bulk store, at most 3
   // floats on either side by hand
-  __device__ __forceinline__ void issue_store(int slot, int t) const {
+  __device__ __forceinline__ void issue_store(int slot, int t, uint64_t pol) const {
     const uint64_t g = reinterpret_cast<uint64_t>(P.grad) + elem_off(t);
     const uint64_t gend = g + gbytes;
     uint64_t g0 = (g + 15) & ~uint64_t(15), g1 = gend & ~uint64_t(15);
     const unsigned char* src = slab(slot) + (g & 15);  // shared-memory image of byte g
     if (g1 > g0) {
-      bulk_s2g(g0, smem_u32(src + (g0 - g)), (uint32_t)(g1 - g0));
+      bulk_s2g_hint(g0, smem_u32(src + (g0 - g)), (uint32_t)(g1 - g0), pol);
     } else {
       g0 = gend; g1 = gend;  // everything by hand
     }
@@ -825,11 +826,14 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
     // ---- phase 1: item a = tile a, this warp's time step t = a*TT + ti (only t < Tg is ever moved)
+    // L2 policies: logits are read once (evict_first); the phase-1 gradient rows must survive in L2 until phase 2
+    // (evict_last); phase 2 reads and rewrites them for the last time (evict_first)
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     uint32_t par = 0;  // bit s = parity of the next completion of this warp's barrier of slot s
     int n = 0;         // items started by this warp (ring position), continues into phase 2
     if (lane == 0) {
       for (int a = 0; a < 2; ++a)
-        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti, P.logits);
+        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti, P.logits, pol_stream);
     }
     for (int it = -1; it < NTg; ++it) {
       const int a = it + 1;
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
         if (lane == 0 && (a + 2) * TT + ti < Tg) {
           // slot of item a+2 was last used by item a-3, whose store was committed three iterations ago
           if (want_grad) PROF_SCOPE(2, bulk_wait_read<1>())
-          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti, P.logits))
+          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti, P.logits, pol_stream))
         }
         if (t < Tg) {
           const int slot = a % NSLOT;
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
           if (want_grad) {
             fence_proxy_async();  // the slab is read by the async proxy (bulk store) next
             __syncwarp();
-            if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t))
+            if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t, pol_keep))
           }
         }
       }
@@ -863,13 +867,13 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
       auto t_of = [&](int i) { return (NTg - 1 - i) * TT + ti; };
       if (lane == 0) {
         for (int i = 0; i < 2 && i < NTg; ++i)
-          if (t_of(i) < Tg) rows.issue_load((n + i) % NSLOT, t_of(i), P.grad);
+          if (t_of(i) < Tg) rows.issue_load((n + i) % NSLOT, t_of(i), P.grad, pol_stream);
       }
       for (int i = -1; i <= NTg; ++i) {
         if (lane == 0 && i >= 0 && i + 2 < NTg && t_of(i + 2) < Tg) {
           // slot of item i+2 was last used by item i-3, whose store was committed two iterations ago
           PROF_SCOPE(2, bulk_wait_read<1>())
-          PROF_SCOPE(3, rows.issue_load((n + i + 2) % NSLOT, t_of(i + 2), P.grad))
+          PROF_SCOPE(3, rows.issue_load((n + i + 2) % NSLOT, t_of(i + 2), P.grad, pol_stream))
         }
         const int ia = i + 1;  // ahead item: emissions
         if (ia < NTg && t_of(ia) < Tg) {
@@ -884,7 +888,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
           PROF_SCOPE(5, rows.scatter_step(t_of(ib), rows.slab(slot), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t_of(ib)))
+          if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t_of(ib), pol_stream))
         }
         NBCTC_ITER_END()
       }

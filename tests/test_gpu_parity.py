@@ -276,3 +276,68 @@ def test_c_abi_host_entry_points(nb):
     rc = lib.nbctc_loss_grad_host_f32(0, p(x), 0, B, Cc, p(lab), lab.shape[1], p(il), p(tl), p(per), p(s64), p(red),
                                       p(g), 1.0, 0)
     assert rc == -1 and b"invalid shape" in lib.nbctc_last_error()
+
+
+def test_long_sequence_accuracy(nb):
+    """T = 4096 (BASELINE configs[3] length): the float64 lattice state keeps the 1e-5 bar."""
+    x, lab, il, tl = make_ctc_case(77, 4096, 2, 64, 200, ragged_T=True)
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl)
+    assert_parity(loss, grad, oracle("ctc", x, lab, il, tl))
+
+
+def _device_call(nb, x, lab, il, tl, seq_w=None, w_scalar=1.0, offset_floats=0):
+    """nbctc_loss_grad_f32 through ctypes with DEVICE pointers (what a non-PyTorch host would do)."""
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    T, B, C = x.shape
+    # optional 4-byte offsets: the logits / gradient pointers are then not 16-byte aligned
+    xs = torch.empty(x.size + offset_floats, device=DEV)
+    xd = xs[offset_floats:].view(T, B, C)
+    xd.copy_(torch.tensor(x))
+    gs = torch.full((x.size + offset_floats,), float("nan"), device=DEV)
+    gd = gs[offset_floats:].view(T, B, C)
+    labd = torch.tensor(lab, device=DEV, dtype=torch.int32)
+    ild, tld = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    per = torch.empty(B, device=DEV)
+    swd = None if seq_w is None else torch.tensor(seq_w, device=DEV, dtype=torch.float32)
+    wsb = int(lib.nbctc_workspace_bytes(T, B, C, lab.shape[1], 0, 0))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
+    rc = lib.nbctc_loss_grad_f32(xd.data_ptr(), T, B, C, labd.data_ptr(), lab.shape[1], ild.data_ptr(), tld.data_ptr(),
+                                 per.data_ptr(), None, None, gd.data_ptr(), None if swd is None else swd.data_ptr(),
+                                 w_scalar, ws.data_ptr(), wsb, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.nbctc_last_error()
+    torch.cuda.synchronize()
+    return per.cpu().double().numpy(), gd.cpu().double().numpy()
+
+
+def test_sequence_weights_zero_and_negative(nb):
+    """w_b = weight_scalar * seq_weights[b] scales the gradient; 0 gives exact zeros and the loss is still right."""
+    x, lab, il, tl = make_ctc_case(21, 50, 6, 37, 9, ragged_T=True, dup=True)
+    sw = np.array([1.0, 0.0, -2.0, 0.5, 0.0, 3.0], np.float32)
+    per, grad = _device_call(nb, x, lab, il, tl, seq_w=sw, w_scalar=0.25)
+    ref = oracle("ctc", x, lab, il, tl, "sum")
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    want = ref["grad"] * (0.25 * sw)[None, :, None]
+    assert rel_l2(grad, want) < TOL
+    assert np.all(grad[:, sw == 0] == 0.0)
+
+
+@pytest.mark.parametrize("off", [1, 2, 3])
+def test_unaligned_tensors_take_the_generic_path(nb, off):
+    """The fused kernel needs 16-byte aligned logits/grad; a 4-byte offset view must still give the right answer."""
+    x, lab, il, tl = make_ctc_case(31, 40, 5, 21, 7, ragged_T=True)
+    per, grad = _device_call(nb, x, lab, il, tl, offset_floats=off)
+    ref = oracle("ctc", x, lab, il, tl, "sum")
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    assert rel_l2(grad, ref["grad"]) < TOL
+
+
+@pytest.mark.parametrize("shape", [(19, 3, 7, 5), (23, 7, 157, 12), (16, 6, 66, 9), (9, 13, 5, 4), (40, 9, 1030, 20)],
+                         ids=lambda s: "T%d_B%d_C%d_L%d" % s)
+def test_slab_alignment_phases(nb, shape):
+    """B*C not a multiple of 4: the 16-byte phase of a time step's rows changes with t; partial last groups;
+    tensors whose byte size is not a multiple of 16."""
+    T, B, C, L = shape
+    x, lab, il, tl = make_ctc_case(500 + T + C, T, B, C, L, ragged_T=True, dup=True)
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl)
+    assert_parity(loss, grad, oracle("ctc", x, lab, il, tl))
