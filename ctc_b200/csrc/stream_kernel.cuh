@@ -36,7 +36,7 @@
 namespace nbctc {
 
 constexpr int kMaxGB = 8;   // sequences per group upper bound (LPR = 4)
-constexpr int kNSlot = 5;   // ring depth (tiles)
+constexpr int kNSlot = 6;   // ring depth (tiles)
 
 struct StreamCfg {
   int NS, Lpad, TT;
@@ -63,7 +63,8 @@ struct Geo {
   static constexpr int AS = Lpad + 8;          // alpha/beta tile row stride (doubles)
   static constexpr int PSEQ = TT * PS + 8;     // p-tile floats per sequence (+8: lane groups hit distinct banks)
   static constexpr int ABSEQ = 2 * TT * AS + 8;  // alpha+beta tile doubles per sequence
-  static constexpr int NTHREADS = 32 * (GB + NRW);
+  static constexpr int NMW = 2;                // mover warps: TMA issue for TT/NMW time steps each
+  static constexpr int NTHREADS = 32 * (GB + NRW + NMW);
 };
 
 int launch_stream_ns2(const Problem& p, const StreamCfg& cfg, cudaStream_t stream);
@@ -798,7 +799,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
         }
       };
       fetch_ckpt(NTg - 1);
-      for (int i = -1; i <= NTg; ++i) {
+      for (int i = -1; i <= NTg + 1; ++i) {
         if (i >= 0 && i < NTg) {
           const int k = NTg - 1 - i;
           if (k < NTb) {
@@ -819,82 +820,102 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
       }
     }
     PROF_DUMP(0)
-  } else {
+  } else if (warp < GB + G::NRW) {
     // ======================================================================== row warp of time step `ti`
     const int ti = warp - GB;
     const int seq = lane / LPR;
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
     // ---- phase 1: item a = tile a, this warp's time step t = a*TT + ti (only t < Tg is ever moved)
-    // L2 policies: logits are read once (evict_first); the phase-1 gradient rows must survive in L2 until phase 2
-    // (evict_last); phase 2 reads and rewrites them for the last time (evict_first)
-    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     uint32_t par = 0;  // bit s = parity of the next completion of this warp's barrier of slot s
-    int n = 0;         // items started by this warp (ring position), continues into phase 2
-    if (lane == 0) {
-      for (int a = 0; a < 2; ++a)
-        if (a * TT + ti < Tg) rows.issue_load(a % NSLOT, a * TT + ti, P.logits, pol_stream);
-    }
     for (int it = -1; it < NTg; ++it) {
       const int a = it + 1;
-      if (a < NTg) {
-        const int t = a * TT + ti;
-        if (lane == 0 && (a + 2) * TT + ti < Tg) {
-          // slot of item a+2 was last used by item a-3, whose store was committed three iterations ago
-          if (want_grad) PROF_SCOPE(2, bulk_wait_read<1>())
-          PROF_SCOPE(3, rows.issue_load((a + 2) % NSLOT, (a + 2) * TT + ti, P.logits, pol_stream))
-        }
-        if (t < Tg) {
-          const int slot = a % NSLOT;
-          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
-          par ^= 1u << slot;
-          PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
-          if (want_grad) {
-            fence_proxy_async();  // the slab is read by the async proxy (bulk store) next
-            __syncwarp();
-            if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t, pol_keep))
-          }
-        }
+      const int t = a * TT + ti;
+      if (a < NTg && t < Tg) {
+        const int slot = a % NSLOT;
+        PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
+        par ^= 1u << slot;
+        PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
+        if (want_grad) fence_proxy_async();  // the slab is read by the async proxy (bulk store) after the barrier
       }
       NBCTC_ITER_END()
     }
-    n = NTg;
     if (want_grad) {
-      // every gradient row of phase 1 is in global memory before phase 2 reads it back
-      if (lane == 0) bulk_wait_all();
-      __syncwarp();
-      // ---- phase 2: item i = tile NTg-1-i at ring position n + i; slabs come back from the gradient tensor
+      // ---- phase 2: item i = tile NTg-1-i at ring position NTg + i; slabs come back from the gradient tensor
       auto t_of = [&](int i) { return (NTg - 1 - i) * TT + ti; };
-      if (lane == 0) {
-        for (int i = 0; i < 2 && i < NTg; ++i)
-          if (t_of(i) < Tg) rows.issue_load((n + i) % NSLOT, t_of(i), P.grad, pol_stream);
-      }
-      for (int i = -1; i <= NTg; ++i) {
-        if (lane == 0 && i >= 0 && i + 2 < NTg && t_of(i + 2) < Tg) {
-          // slot of item i+2 was last used by item i-3, whose store was committed two iterations ago
-          PROF_SCOPE(2, bulk_wait_read<1>())
-          PROF_SCOPE(3, rows.issue_load((n + i + 2) % NSLOT, t_of(i + 2), P.grad, pol_stream))
-        }
+      for (int i = -1; i <= NTg + 1; ++i) {
         const int ia = i + 1;  // ahead item: emissions
         if (ia < NTg && t_of(ia) < Tg) {
-          const int slot = (n + ia) % NSLOT;
+          const int slot = (NTg + ia) % NSLOT;
           PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
           par ^= 1u << slot;
           PROF_SCOPE(4, rows.emit_step(t_of(ia), rows.slab(slot), S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
         }
-        const int ib = i - 1;  // behind item: gamma scatter, slab back to the gradient tensor
-        if (ib >= 0 && t_of(ib) < Tg) {
-          const int slot = (n + ib) % NSLOT;
+        const int ib = i - 1;  // behind item: gamma scatter into the slab
+        if (ib >= 0 && ib < NTg && t_of(ib) < Tg) {
+          const int slot = (NTg + ib) % NSLOT;
           PROF_SCOPE(5, rows.scatter_step(t_of(ib), rows.slab(slot), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) PROF_SCOPE(3, rows.issue_store(slot, t_of(ib), pol_stream))
         }
         NBCTC_ITER_END()
       }
-      if (lane == 0) bulk_wait_all();  // the ring must outlive the last bulk store's reads; rows final before the tail
     }
     PROF_DUMP(1)
+  } else {
+    // ======================================================================== mover warp: TMA for TT/NMW time steps
+    // Lane l moves time step ti of every tile: loads two items ahead of the row warps, stores one iteration
+    // behind them (after the barrier that ends the row warp's work on the slab).  L2 policies: logits are read
+    // once (evict_first); the phase-1 gradient rows must survive in L2 until phase 2 (evict_last); phase 2 reads
+    // and rewrites them for the last time (evict_first).
+    constexpr int PER = TT / G::NMW;
+    const int ti = (warp - GB - G::NRW) * PER + lane;
+    const bool mine = lane < PER;
+    const Rows<NS, LPR, CPL> mv(P, cfg, S, lane, mine ? ti : 0, gcnt, b0, 0.f);
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    if (mine) {
+      for (int a = 0; a < 3 && a < NTg; ++a)
+        if (a * TT + ti < Tg) mv.issue_load(a % NSLOT, a * TT + ti, P.logits, pol_stream);
+    }
+    for (int it = -1; it < NTg; ++it) {
+      if (mine) {
+        // item `it` was finished by its row warp in the previous iteration
+        if (want_grad && it >= 0) {
+          if (it * TT + ti < Tg) PROF_SCOPE(0, mv.issue_store(it % NSLOT, it * TT + ti, pol_keep))
+          else bulk_commit();
+        }
+        // slot of item it+3 was last used by item it-3, stored three iterations ago
+        if (it >= 0 && it + 3 < NTg && (it + 3) * TT + ti < Tg) {
+          if (want_grad) PROF_SCOPE(1, bulk_wait_read<2>())
+          PROF_SCOPE(2, mv.issue_load((it + 3) % NSLOT, (it + 3) * TT + ti, P.logits, pol_stream))
+        }
+      }
+      NBCTC_ITER_END()
+    }
+    if (want_grad) {
+      auto t_of = [&](int i) { return (NTg - 1 - i) * TT + ti; };
+      if (mine) {
+        bulk_wait_all();  // every gradient row of phase 1 is in global memory before it is read back
+        for (int i = 0; i < 2 && i < NTg; ++i)
+          if (t_of(i) < Tg) mv.issue_load((NTg + i) % NSLOT, t_of(i), P.grad, pol_stream);
+      }
+      for (int i = -1; i <= NTg + 1; ++i) {
+        if (mine) {
+          const int is = i - 2;  // item whose slab got its gamma in the previous iteration
+          if (is >= 0) {
+            if (t_of(is) < Tg) PROF_SCOPE(0, mv.issue_store((NTg + is) % NSLOT, t_of(is), pol_stream))
+            else bulk_commit();
+          }
+          // slot of item i+2 was last used by item i-4, stored two iterations ago
+          if (i >= 0 && i + 2 < NTg && t_of(i + 2) < Tg) {
+            PROF_SCOPE(1, bulk_wait_read<2>())
+            PROF_SCOPE(2, mv.issue_load((NTg + i + 2) % NSLOT, t_of(i + 2), P.grad, pol_stream))
+          }
+        }
+        NBCTC_ITER_END()
+      }
+      if (mine) bulk_wait_all();  // the ring must outlive the last bulk store's reads; rows final before the tail
+    }
+    PROF_DUMP(2)
   }
 #undef NBCTC_ITER_END
 

@@ -53,7 +53,8 @@ trace = pall[24:].reshape(160, 32, 2)
 groups = (B + GB - 1) // GB
 names = {
     0: ("chain", GB, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
-    1: ("row", NRW, ["wait rows", "forward step", "wait store reads", "TMA issue", "gather commit", "scatter", "barrier", "total"]),
+    1: ("row", NRW, ["wait rows", "forward step", "-", "-", "emit (ph2)", "scatter", "barrier", "total"]),
+    2: ("mover", 2, ["store issue", "wait store reads", "load issue", "-", "-", "-", "barrier", "total"]),
 }
 print(f"workload {name}: GB={GB} NRW={NRW} groups={groups} kernel {e0.elapsed_time(e1):.3f} ms (instrumented); "
       f"mean cycles per warp per CTA")
@@ -62,7 +63,7 @@ for role, (rn, nw, nm) in names.items():
     print(f"  {rn:9s} " + "  ".join(f"{n}={v:,.0f}" for n, v in zip(nm, m) if n != "-"))
 
 # per-iteration trace of the middle CTA: cycles each role spends working in the iteration (work end - previous barrier end)
-nw = GB + NRW
+nw = GB + NRW + 2
 prev = np.zeros(nw)
 print("trace of one CTA: iteration | iteration cycles | busy cycles chain(max) rows(max)")
 for itx in range(160):
@@ -70,5 +71,5 @@ for itx in range(160):
         break
     busy = trace[itx, :nw, 0] - prev
     end = trace[itx, :nw, 1]
-    print(f"  it={itx:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f}")
+    print(f"  it={itx:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f} movers={busy[GB + NRW:].max():6.0f}")
     prev = end
