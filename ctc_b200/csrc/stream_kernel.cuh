@@ -506,6 +506,24 @@ struct Rows {
     return v;
   }
 
+  // Chunk slot c of a single-segment row is chunk q = li + c*LPR.  CPL <= ceil(nch_max/LPR) + 1 and nch varies by
+  // at most one between the rows of a group, so the slots c <= CPL-3 always hold a full chunk of the row that is
+  // not its last one: no bounds check, no tail handling (the head chunk is slot 0 of lane 0).
+  static __device__ __forceinline__ constexpr bool slot_is_inner(int c) { return c + 3 <= CPL; }
+  __device__ __forceinline__ float4 load_slot(const RowGeom& g, int c) const {
+    const int q = li + c * LPR;
+    if (slot_is_inner(c)) {
+      float4 v = g.srow[q];
+      if (c == 0 && li == 0) mask_head(v, g.off4);
+      return v;
+    }
+    return load_chunk(g, q);
+  }
+  __device__ __forceinline__ void store_slot(const RowGeom& g, int c, const float4& y) const {
+    const int q = li + c * LPR;
+    if (slot_is_inner(c) && c > 0) g.srow[q] = y;
+    else store_chunk(g, q, y);
+  }
   // chunk q of the row -> registers, floats of neighbouring rows (and chunks beyond the row) as -inf
   __device__ __forceinline__ float4 load_chunk(const RowGeom& g, int q) const {
     float4 v = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
@@ -537,7 +555,7 @@ struct Rows {
     if (cfg.NSEG == 1) {
       float4 v[CPL];
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) v[c] = load_chunk(g, li + c * LPR);
+      for (int c = 0; c < CPL; ++c) v[c] = load_slot(g, c);
       float m_l = kNegInf;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) m_l = fmaxf(m_l, fmaxf(fmaxf(v[c].x, v[c].y), fmaxf(v[c].z, v[c].w)));
@@ -555,7 +573,7 @@ struct Rows {
       const float s = group_sum(((s0 + s1) + (s2 + s3)) * cf);
       const float sc = act ? weff * cf / s : 0.f;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) store_chunk(g, li + c * LPR, scale4(v[c], sc));
+      for (int c = 0; c < CPL; ++c) store_slot(g, c, scale4(v[c], sc));
     } else {
       // long rows: online max/sum over the segments, then a second pass over the slab
       float m_l = kNegInf, s_l = 0.f;
@@ -646,10 +664,17 @@ struct Rows {
     const int nr = __reduce_max_sync(0xffffffffu, live ? max_rank : 0);
     for (int r = 0; r <= nr; ++r) {
       if (live) {
+        // the addresses of one round are pairwise distinct: all loads first, then all stores
+        float cur[NSL];
 #pragma unroll
         for (int j = 0; j < NSL; ++j) {
           const int l = label(j);
-          if (l >= 0 && (l >> kLabBits) == r) yr[l & kLabMask] += gam[j];
+          cur[j] = (l >= 0 && (l >> kLabBits) == r) ? yr[l & kLabMask] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NSL; ++j) {
+          const int l = label(j);
+          if (l >= 0 && (l >> kLabBits) == r) yr[l & kLabMask] = cur[j] + gam[j];
         }
       }
       if (r < nr) __syncwarp();
