@@ -232,19 +232,40 @@ __device__ __forceinline__ void load_p(const float* row, int hl, bool rev, doubl
   for (int j = 0; j < NS; ++j) p[j] = (double)(rev ? t[NS - 1 - j] : t[j]);
 }
 
-// x(s) <- (x(s) + x(s-1)) * p(s) in the lane's (possibly reversed) state order; `sum` keeps the pre-emission value.
-// alpha: x = alpha (NoBlankCTC.py:73-85).  beta half: x(s) = beta_t(s) p_t(s), sum = beta_t(s).
-// `carry` enters position 0 of the half (the virtual start state: NoBlankCTC.py:92-93 and the t>0 guard at :75).
-template <int NS>
-__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double& carry) {
+// x(s) <- (x(s) + x(s-1)) * p(s) in the lane's (possibly reversed) state order, written as
+// x(s) <- fma(x(s-1), p(s), x(s)*p(s)): the products x(s)*p(s) do not wait for the neighbour lane's state, so the
+// dependent path of a step is one shuffle + one DFMA for the lane's first state and one DFMA for the others
+// (a shuffle, a DADD and a DMUL in the textbook form).  alpha: x = alpha (NoBlankCTC.py:73-85).  beta half:
+// x(s) = beta_t(s) p_t(s) and, with kSum, sum(s) = x(s) + x(s-1) = beta_t(s) (off the dependent path).
+// kFirst: first step of a tile -- `carry` enters position 0 of the half (the virtual start state:
+// NoBlankCTC.py:92-93 and the t>0 guard at :75); in every other step position 0 of lane 0 has no neighbour.
+template <int NS, bool kSum, bool kFirst>
+__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry) {
+  double t[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) t[j] = x[j] * p[j];
   double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
-  if (hl == 0) up = carry;
-  carry = 0.0;
+  double p0 = p[0];
+  if (kFirst) {
+    if (hl == 0) up = carry;
+  } else {
+    if (hl == 0) p0 = 0.0;  // lane 0's shuffle result is its own (finite) value: times 0
+  }
+  if (kSum) {
 #pragma unroll
-  for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
-  sum[0] = x[0] + up;
+    for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
+    sum[0] = x[0] + ((kFirst || hl != 0) ? up : 0.0);
+  }
 #pragma unroll
-  for (int j = 0; j < NS; ++j) x[j] = sum[j] * p[j];
+  for (int j = NS - 1; j >= 1; --j) x[j] = fma(x[j - 1], p[j], t[j]);
+  x[0] = fma(up, p0, t[0]);
+}
+// run-time `first` (generic loops)
+template <int NS, bool kSum>
+__device__ __forceinline__ void chain_step_rt(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry,
+                                              bool first) {
+  if (first) chain_step<NS, kSum, true>(x, sum, p, hl, carry);
+  else chain_step<NS, kSum, false>(x, sum, p, hl, 0.0);
 }
 
 // Chain-warp state lives in plain registers of the kernel body (passed by reference to force-inlined functions).
@@ -274,15 +295,19 @@ __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int 
 #pragma unroll
     for (int i = 0; i < TT; ++i) load_p<NS>(pt + i * PS, hl, false, pr[i]);
 #pragma unroll
-    for (int i = 0; i < TT; ++i) chain_step<NS>(x, sum, pr[i], hl, c.carry);
+    for (int i = 0; i < TT; ++i) {
+      if (i == 0) chain_step<NS, false, true>(x, sum, pr[i], hl, c.carry);
+      else chain_step<NS, false, false>(x, sum, pr[i], hl, 0.0);
+    }
   } else {
 #pragma unroll 2
     for (int i = 0; i < nv; ++i) {
       double pf[NS];
       load_p<NS>(pt + i * PS, hl, false, pf);
-      chain_step<NS>(x, sum, pf, hl, c.carry);
+      chain_step_rt<NS, false>(x, sum, pf, hl, c.carry, i == 0);
     }
   }
+  c.carry = 0.0;
 }
 
 // ---- read-out after the sequence's last phase-1 tile (NoBlankCTC.py:58-68,:139) + beta start state
@@ -347,7 +372,8 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
 #pragma unroll
     for (int jj = 0; jj < TT; ++jj) {
       const int i = isb ? (TT - 1 - jj) : jj;  // alpha walks up the tile, beta walks down
-      chain_step<NS>(x, sum, pr[jj], hl, c.carry);
+      if (jj == 0) chain_step<NS, true, true>(x, sum, pr[jj], hl, c.carry);
+      else chain_step<NS, true, false>(x, sum, pr[jj], hl, 0.0);
 #pragma unroll
       for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
     }
@@ -357,11 +383,12 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
       const int i = isb ? (nv - 1 - jj) : jj;
       double pf[NS];
       load_p<NS>(pt + i * PS, hl, isb, pf);
-      chain_step<NS>(x, sum, pf, hl, c.carry);
+      chain_step_rt<NS, true>(x, sum, pf, hl, c.carry, jj == 0);
 #pragma unroll
       for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
     }
   }
+  c.carry = 0.0;
   // every lane takes part in the half-wide shuffles; only the beta half keeps the result
   const int e = rescale_half<NS>(x);
   if (isb) c.Eb += e;
