@@ -63,7 +63,7 @@ struct Geo {
   static constexpr int AS = Lpad + 8;          // alpha/beta tile row stride (doubles)
   static constexpr int PSEQ = TT * PS + 8;     // p-tile floats per sequence (+8: lane groups hit distinct banks)
   static constexpr int ABSEQ = 2 * TT * AS + 8;  // alpha+beta tile doubles per sequence
-  static constexpr int NMW = 2;                // mover warps: TMA issue for TT/NMW time steps each
+  static constexpr int NMW = 2;              // mover warps: TMA issue for TT/NMW time steps each
   static constexpr int NTHREADS = 32 * (GB + NRW + NMW);
 };
 
@@ -442,6 +442,7 @@ struct Rows {
   const float wgt;          // gradient weight of the sequence; weff = wgt, or 1 where wgt == 0 (see kernel tail)
   const float weff, winv;
   const int* lab_seq;
+  const int ph_fixed;       // slab phase if it does not depend on t, else -1
   int labr[kLabRegs ? NSL : 1];  // this lane's labels (-1 = no state)
 
   __device__ __forceinline__ Rows(const Problem& P_, const StreamCfg& cfg_, const Smem& S_, int lane_, int ti_, int gcnt_,
@@ -449,7 +450,8 @@ struct Rows {
       : P(P_), cfg(cfg_), S(S_), lane(lane_), li(lane_ & (LPR - 1)), seq(lane_ / LPR), ti(ti_), gcnt(gcnt_), b0(b0_),
         Tb(S_.info[lane_ / LPR]), Lb(S_.info[kMaxGB + lane_ / LPR]), C((int)P_.C), max_rank(S_.info[3 * kMaxGB + lane_ / LPR]),
         gbytes((uint32_t)gcnt_ * (uint32_t)P_.C * 4u), wgt(wgt_), weff(wgt_ != 0.f ? wgt_ : 1.f),
-        winv(1.f / (wgt_ != 0.f ? wgt_ : 1.f)), lab_seq(S_.lab + (lane_ / LPR) * Lpad) {
+        winv(1.f / (wgt_ != 0.f ? wgt_ : 1.f)), lab_seq(S_.lab + (lane_ / LPR) * Lpad),
+        ph_fixed((((unsigned)P_.B * (unsigned)P_.C) & 3u) == 0 ? (int)((((unsigned)b0_ & 3u) * ((unsigned)P_.C & 3u)) & 3u) : -1) {
     if constexpr (kLabRegs) {
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
@@ -467,6 +469,7 @@ struct Rows {
   __device__ __forceinline__ uint64_t elem_off(int t) const { return (((uint64_t)t * P.B + b0) * P.C) * 4u; }
   // float index (0..3) of the slab's first element inside its first 16-byte chunk (both tensors are 16-byte aligned)
   __device__ __forceinline__ int slab_phase(int t) const {
+    if (ph_fixed >= 0) return ph_fixed;  // B*C % 4 == 0: the same phase at every time step
     return (int)(((((unsigned)t & 3u) * ((unsigned)P.B & 3u) + ((unsigned)b0 & 3u)) * ((unsigned)C & 3u)) & 3u);
   }
   __device__ __forceinline__ unsigned char* slab(int slot) const { return S.ring + ((size_t)slot * TT + ti) * cfg.RSg; }
@@ -880,34 +883,43 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
     // ---- phase 1: item a = tile a, this warp's time step t = a*TT + ti (only t < Tg is ever moved)
     uint32_t par = 0;  // bit s = parity of the next completion of this warp's barrier of slot s
+    int slot_a = 0;    // ring slot of the item the ahead stage works on (ring position = items since the start)
     for (int it = -1; it < NTg; ++it) {
       const int a = it + 1;
       const int t = a * TT + ti;
-      if (a < NTg && t < Tg) {
-        const int slot = a % NSLOT;
-        PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
-        par ^= 1u << slot;
-        PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
-        if (want_grad) fence_proxy_async();  // the slab is read by the async proxy (bulk store) after the barrier
+      if (a < NTg) {
+        if (t < Tg) {
+          PROF_SCOPE(0, mbar_wait(&S.sfull[slot_a * TT + ti], (par >> slot_a) & 1u))
+          par ^= 1u << slot_a;
+          PROF_SCOPE(1, rows.forward_step(t, rows.slab(slot_a), S.ptile + (size_t)((a & 1) * GB) * G::PSEQ))
+          if (want_grad) fence_proxy_async();  // the slab is read by the async proxy (bulk store) after the barrier
+        }
+        slot_a = slot_a + 1 == NSLOT ? 0 : slot_a + 1;
       }
       NBCTC_ITER_END()
     }
     if (want_grad) {
       // ---- phase 2: item i = tile NTg-1-i at ring position NTg + i; slabs come back from the gradient tensor
-      auto t_of = [&](int i) { return (NTg - 1 - i) * TT + ti; };
+      int slot_b = slot_a;          // ring slot of the behind stage's item (two items behind the ahead stage)
       for (int i = -1; i <= NTg + 1; ++i) {
         const int ia = i + 1;  // ahead item: emissions
-        if (ia < NTg && t_of(ia) < Tg) {
-          const int slot = (NTg + ia) % NSLOT;
-          PROF_SCOPE(0, mbar_wait(&S.sfull[slot * TT + ti], (par >> slot) & 1u))
-          par ^= 1u << slot;
-          PROF_SCOPE(4, rows.emit_step(t_of(ia), rows.slab(slot), S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
+        if (ia < NTg) {
+          const int ta = (NTg - 1 - ia) * TT + ti;
+          if (ta < Tg) {
+            PROF_SCOPE(0, mbar_wait(&S.sfull[slot_a * TT + ti], (par >> slot_a) & 1u))
+            par ^= 1u << slot_a;
+            PROF_SCOPE(4, rows.emit_step(ta, rows.slab(slot_a), S.ptile + (size_t)((ia & 1) * GB) * G::PSEQ))
+          }
+          slot_a = slot_a + 1 == NSLOT ? 0 : slot_a + 1;
         }
         const int ib = i - 1;  // behind item: gamma scatter into the slab
-        if (ib >= 0 && ib < NTg && t_of(ib) < Tg) {
-          const int slot = (NTg + ib) % NSLOT;
-          PROF_SCOPE(5, rows.scatter_step(t_of(ib), rows.slab(slot), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
-          fence_proxy_async();
+        if (ib >= 0 && ib < NTg) {
+          const int tb = (NTg - 1 - ib) * TT + ti;
+          if (tb < Tg) {
+            PROF_SCOPE(5, rows.scatter_step(tb, rows.slab(slot_b), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
+            fence_proxy_async();
+          }
+          slot_b = slot_b + 1 == NSLOT ? 0 : slot_b + 1;
         }
         NBCTC_ITER_END()
       }
