@@ -7,6 +7,8 @@
 //   K2 lattice  : one CTA per sequence, thread = state, float64 log domain alpha then beta,
 //                 gamma overwrites the emission tile (NoBlankCTC.py:71-87 transition, :58-68 read-out)
 //   K3 grad     : one warp per (t,b) row -> w*(softmax - scatter(gamma)) / w*(sigmoid - gamma.y)/C
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nbctc {
@@ -213,6 +215,112 @@ grad_kernel(Problem p, GenericWs w) {
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Binary variant with the sequence's multi-hot rows cached in shared memory.  One CTA = one sequence and a chunk
+// of kBinTCh time steps; y[b] (L_b x C) is read from HBM once per CTA instead of once per (t,b) row.
+// ys[s*Cp + c] with Cp odd: lanes that walk s (emissions) and lanes that walk c (gradient) are both conflict-free.
+constexpr int kBinTCh = 32;
+
+__device__ __forceinline__ void bin_load_targets(const Problem& p, int64_t b, int Lb, int Cp, float* ys) {
+  const float* y = p.targets + b * p.Lmax * p.C;
+  for (int64_t i = threadIdx.x; i < (int64_t)Lb * p.C; i += blockDim.x) {
+    const int s = (int)(i / p.C), c = (int)(i - (int64_t)s * p.C);
+    ys[s * Cp + c] = y[i];
+  }
+}
+
+// emissions e[t,b,s] = (1/C) y_s . x_t and the row constant (1/C) sum_c softplus(x_c) (NoBlankBinaryCTC.py:109-112)
+__global__ void __launch_bounds__(kRowWarps * 32)
+rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
+  extern __shared__ float smf[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
+  if (!seq_feasible(Tb, Lb64, p.T, p.Lmax)) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) w.bad[b] = 1;
+    return;
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) w.bad[b] = 0;
+  const int Lb = (int)Lb64, C = (int)p.C;
+  float* ys = smf;                              // [Lb][Cp]
+  float* xs = smf + (size_t)Lb * Cp + warp * C; // this warp's logits row
+  bin_load_targets(p, b, Lb, Cp, ys);
+  __syncthreads();
+  const float invC = 1.f / (float)C;
+  const int64_t t0 = (int64_t)blockIdx.y * kBinTCh;
+  for (int64_t t = t0 + warp; t < min(t0 + kBinTCh, Tb); t += kRowWarps) {
+    const int64_t row = t * p.B + b;
+    const float* x = p.logits + row * C;
+    float sp = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = x[c];
+      xs[c] = v;
+      sp += fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+    }
+    sp = warp_sum(sp);
+    if (lane == 0) w.rowc[row] = sp * invC;
+    __syncwarp();
+    for (int s0 = 0; s0 < Lb; s0 += 32) {
+      const int st = s0 + lane;
+      const float* yr = ys + (size_t)min(st, Lb - 1) * Cp;
+      float d0 = 0.f, d1 = 0.f;
+      int c = 0;
+      for (; c + 1 < C; c += 2) {
+        d0 = fmaf(yr[c], xs[c], d0);
+        d1 = fmaf(yr[c + 1], xs[c + 1], d1);
+      }
+      if (c < C) d0 = fmaf(yr[c], xs[c], d0);
+      if (st < Lb) w.emis[row * p.Lmax + st] = (d0 + d1) * invC;
+    }
+    __syncwarp();
+  }
+}
+
+// grad[t,b,c] = w/C * (sigmoid(x) - sum_s gamma_t(s) y[b,s,c])
+__global__ void __launch_bounds__(kRowWarps * 32)
+grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
+  extern __shared__ float smf[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
+  const int C = (int)p.C;
+  const int64_t t0 = (int64_t)blockIdx.y * kBinTCh;
+  const int64_t t1 = min(t0 + kBinTCh, p.T);
+  const float lossb = p.loss[b];
+  const bool ok = seq_feasible(Tb, Lb64, p.T, p.Lmax) && (lossb < INFINITY);
+  const int64_t tlive = ok ? min(t1, Tb) : t0;  // rows [tlive, t1) are zeros
+  for (int64_t t = max(t0, tlive) + warp; t < t1; t += kRowWarps) {
+    float* g = p.grad + (t * p.B + b) * C;
+    for (int c = lane; c < C; c += 32) g[c] = 0.f;
+  }
+  if (!ok || t0 >= Tb) return;
+  const int Lb = (int)Lb64;
+  float* ys = smf;                                           // [Lb][Cp]
+  float* gs = smf + (size_t)Lb * Cp + warp * (int)p.Lmax;    // this warp's gamma row
+  bin_load_targets(p, b, Lb, Cp, ys);
+  __syncthreads();
+  const float wgt = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f) / (float)C;
+  for (int64_t t = t0 + warp; t < tlive; t += kRowWarps) {
+    const int64_t row = t * p.B + b;
+    const float* x = p.logits + row * C;
+    const float* gam = w.emis + row * p.Lmax;
+    for (int s = lane; s < Lb; s += 32) gs[s] = gam[s];
+    __syncwarp();
+    float* g = p.grad + row * C;
+    for (int c = lane; c < C; c += 32) {
+      float a0 = 1.f / (1.f + expf(-x[c])), a1 = 0.f;
+      int s = 0;
+      for (; s + 1 < Lb; s += 2) {
+        a0 = fmaf(-gs[s], ys[s * Cp + c], a0);
+        a1 = fmaf(-gs[s + 1], ys[(s + 1) * Cp + c], a1);
+      }
+      if (s < Lb) a0 = fmaf(-gs[s], ys[s * Cp + c], a0);
+      g[c] = wgt * (a0 + a1);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void reduce_loss_kernel(const float* __restrict__ loss, const float* __restrict__ seq_w, float w_scalar,
                                    int64_t B, double* __restrict__ sum_out, float* __restrict__ reduced_out) {
   // one CTA, fixed-order tree => bit-reproducible
@@ -264,10 +372,21 @@ int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cud
   }
   const int64_t rows = p.T * p.B;
   const unsigned row_blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
-  if (binary)
+  // binary variant: the sequence's multi-hot rows are cached in shared memory when they fit
+  const int Cp = (int)(p.C | 1);
+  const size_t bin_smem_rs = sizeof(float) * ((size_t)p.Lmax * Cp + (size_t)kRowWarps * p.C);
+  const size_t bin_smem_gr = sizeof(float) * ((size_t)p.Lmax * Cp + (size_t)kRowWarps * p.Lmax);
+  const bool bin_smem = binary && std::max(bin_smem_rs, bin_smem_gr) <= 200 * 1024;
+  const dim3 bin_grid((unsigned)p.B, (unsigned)((p.T + kBinTCh - 1) / kBinTCh));
+  if (bin_smem) {
+    if (bin_smem_rs > 48 * 1024)
+      NBCTC_CUDA_CHECK(cudaFuncSetAttribute(rowstats_bin_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_rs));
+    rowstats_bin_smem_kernel<<<bin_grid, kRowWarps * 32, bin_smem_rs, stream>>>(p, w, Cp);
+  } else if (binary) {
     rowstats_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
-  else
+  } else {
     rowstats_kernel<false><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
+  }
   NBCTC_LAUNCH_CHECK();
 
   int nt = (int)std::min<int64_t>(1024, (p.Lmax + 31) / 32 * 32);
@@ -278,7 +397,11 @@ int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cud
   NBCTC_LAUNCH_CHECK();
 
   if (p.grad) {
-    if (binary)
+    if (bin_smem) {
+      if (bin_smem_gr > 48 * 1024)
+        NBCTC_CUDA_CHECK(cudaFuncSetAttribute(grad_bin_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_gr));
+      grad_bin_smem_kernel<<<bin_grid, kRowWarps * 32, bin_smem_gr, stream>>>(p, w, Cp);
+    } else if (binary)
       grad_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
     else
       grad_kernel<false><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
