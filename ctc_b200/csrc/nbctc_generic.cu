@@ -153,8 +153,8 @@ lattice_kernel(Problem p, GenericWs w) {
     for (int64_t s = threadIdx.x; s < Lb; s += nt) {
       double beta = (s == Lb - 1) ? 0.0 : -INFINITY;
       double e = (double)w.emis[row * L + s] - rc;
-      double g = exp(w.alpha[row * L + s] + beta - ll);
-      w.emis[row * L + s] = (float)g;
+      float g = expf((float)(w.alpha[row * L + s] + beta - ll));
+      w.emis[row * L + s] = g;
       a0[s] = beta + e;
     }
     __syncthreads();
@@ -169,8 +169,8 @@ lattice_kernel(Problem p, GenericWs w) {
       double up = (s + 1 < Lb) ? prev[s + 1] : -INFINITY;
       double beta = logaddexp64(prev[s], up);
       double e = (double)w.emis[row * L + s] - rc;
-      double g = exp(w.alpha[row * L + s] + beta - ll);
-      w.emis[row * L + s] = (float)g;
+      float g = expf((float)(w.alpha[row * L + s] + beta - ll));
+      w.emis[row * L + s] = g;
       cur[s] = beta + e;
     }
     __syncthreads();
