@@ -219,14 +219,54 @@ grad_kernel(Problem p, GenericWs w) {
 // Binary variant with the sequence's multi-hot rows cached in shared memory.  One CTA = one sequence and a chunk
 // of kBinTCh time steps; y[b] (L_b x C) is read from HBM once per CTA instead of once per (t,b) row.
 // ys[s*Cp + c] with Cp odd: lanes that walk s (emissions) and lanes that walk c (gradient) are both conflict-free.
-constexpr int kBinTCh = 32;
+// When every entry of y[b] is exactly 0 or 1 (multi-hot, the reference's dataset: charades_ctc_pred.py:538-559) the
+// dot products run over bit masks of the non-zero entries instead (state -> classes for the emissions, class ->
+// states for the gradient); soft targets take the dense loops.
+constexpr int kBinTCh = 128;
 
-__device__ __forceinline__ void bin_load_targets(const Problem& p, int64_t b, int Lb, int Cp, float* ys) {
+struct BinSmem {
+  float* ys;        // [Lb][Cp]
+  unsigned* smask;  // [Lb][CW]  classes of state s
+  unsigned* cmask;  // [C][LW]   states that contain class c
+  int* soft;        // != 0: some entry is neither 0 nor 1
+  float* scratch;   // per-warp row buffer
+};
+__host__ __device__ inline size_t bin_smem_floats(int64_t Lmax, int64_t C, int Cp, int64_t per_warp) {
+  const int64_t CW = (C + 31) / 32, LW = (Lmax + 31) / 32;
+  return (size_t)(Lmax * Cp + Lmax * CW + C * LW + 4 + kRowWarps * per_warp);
+}
+__device__ __forceinline__ BinSmem bin_setup(const Problem& p, int64_t b, int Lb, int Cp, float* smf, int64_t per_warp) {
+  const int C = (int)p.C, CW = (C + 31) / 32, LW = (Lb + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  BinSmem S;
+  S.ys = smf;
+  S.smask = reinterpret_cast<unsigned*>(smf + (size_t)p.Lmax * Cp);
+  S.cmask = S.smask + (size_t)p.Lmax * CW;
+  S.soft = reinterpret_cast<int*>(S.cmask + (size_t)C * ((p.Lmax + 31) / 32));
+  S.scratch = reinterpret_cast<float*>(S.soft + 4) + (size_t)warp * per_warp;
+  if (threadIdx.x == 0) *S.soft = 0;
   const float* y = p.targets + b * p.Lmax * p.C;
-  for (int64_t i = threadIdx.x; i < (int64_t)Lb * p.C; i += blockDim.x) {
-    const int s = (int)(i / p.C), c = (int)(i - (int64_t)s * p.C);
-    ys[s * Cp + c] = y[i];
+  for (int64_t i = threadIdx.x; i < (int64_t)Lb * C; i += blockDim.x) {
+    const int s = (int)(i / C), c = (int)(i - (int64_t)s * C);
+    S.ys[s * Cp + c] = y[i];
   }
+  __syncthreads();
+  int soft = 0;
+  for (int i = warp; i < Lb * CW; i += kRowWarps) {  // state -> classes
+    const int s = i / CW, wd = i - s * CW, c = wd * 32 + lane;
+    const float v = c < C ? S.ys[s * Cp + c] : 0.f;
+    soft |= (v != 0.f && v != 1.f);
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+    if (lane == 0) S.smask[s * CW + wd] = m;
+  }
+  for (int i = warp; i < C * LW; i += kRowWarps) {   // class -> states
+    const int c = i / LW, wd = i - c * LW, st = wd * 32 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, st < Lb && S.ys[st * Cp + c] != 0.f);
+    if (lane == 0) S.cmask[c * LW + wd] = m;
+  }
+  if (soft) atomicOr(S.soft, 1);
+  __syncthreads();
+  return S;
 }
 
 // emissions e[t,b,s] = (1/C) y_s . x_t and the row constant (1/C) sum_c softplus(x_c) (NoBlankBinaryCTC.py:109-112)
@@ -241,13 +281,13 @@ rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
     return;
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) w.bad[b] = 0;
-  const int Lb = (int)Lb64, C = (int)p.C;
-  float* ys = smf;                              // [Lb][Cp]
-  float* xs = smf + (size_t)Lb * Cp + warp * C; // this warp's logits row
-  bin_load_targets(p, b, Lb, Cp, ys);
-  __syncthreads();
-  const float invC = 1.f / (float)C;
   const int64_t t0 = (int64_t)blockIdx.y * kBinTCh;
+  if (t0 >= Tb) return;
+  const int Lb = (int)Lb64, C = (int)p.C, CW = (C + 31) / 32;
+  const BinSmem S = bin_setup(p, b, Lb, Cp, smf, C);
+  float* xs = S.scratch;  // this warp's logits row
+  const bool soft = *S.soft != 0;
+  const float invC = 1.f / (float)C;
   for (int64_t t = t0 + warp; t < min(t0 + kBinTCh, Tb); t += kRowWarps) {
     const int64_t row = t * p.B + b;
     const float* x = p.logits + row * C;
@@ -262,14 +302,24 @@ rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
     __syncwarp();
     for (int s0 = 0; s0 < Lb; s0 += 32) {
       const int st = s0 + lane;
-      const float* yr = ys + (size_t)min(st, Lb - 1) * Cp;
       float d0 = 0.f, d1 = 0.f;
-      int c = 0;
-      for (; c + 1 < C; c += 2) {
-        d0 = fmaf(yr[c], xs[c], d0);
-        d1 = fmaf(yr[c + 1], xs[c + 1], d1);
+      if (soft) {
+        const float* yr = S.ys + (size_t)min(st, Lb - 1) * Cp;
+        int c = 0;
+        for (; c + 1 < C; c += 2) {
+          d0 = fmaf(yr[c], xs[c], d0);
+          d1 = fmaf(yr[c + 1], xs[c + 1], d1);
+        }
+        if (c < C) d0 = fmaf(yr[c], xs[c], d0);
+      } else if (st < Lb) {
+        for (int wd = 0; wd < CW; ++wd) {
+          unsigned m = S.smask[st * CW + wd];
+          while (m) {
+            d0 += xs[wd * 32 + __ffs(m) - 1];
+            m &= m - 1;
+          }
+        }
       }
-      if (c < C) d0 = fmaf(yr[c], xs[c], d0);
       if (st < Lb) w.emis[row * p.Lmax + st] = (d0 + d1) * invC;
     }
     __syncwarp();
@@ -294,11 +344,10 @@ grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
     for (int c = lane; c < C; c += 32) g[c] = 0.f;
   }
   if (!ok || t0 >= Tb) return;
-  const int Lb = (int)Lb64;
-  float* ys = smf;                                           // [Lb][Cp]
-  float* gs = smf + (size_t)Lb * Cp + warp * (int)p.Lmax;    // this warp's gamma row
-  bin_load_targets(p, b, Lb, Cp, ys);
-  __syncthreads();
+  const int Lb = (int)Lb64, LW = (Lb + 31) / 32;
+  const BinSmem S = bin_setup(p, b, Lb, Cp, smf, p.Lmax);
+  float* gs = S.scratch;  // this warp's gamma row
+  const bool soft = *S.soft != 0;
   const float wgt = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f) / (float)C;
   for (int64_t t = t0 + warp; t < tlive; t += kRowWarps) {
     const int64_t row = t * p.B + b;
@@ -309,12 +358,22 @@ grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
     float* g = p.grad + row * C;
     for (int c = lane; c < C; c += 32) {
       float a0 = 1.f / (1.f + expf(-x[c])), a1 = 0.f;
-      int s = 0;
-      for (; s + 1 < Lb; s += 2) {
-        a0 = fmaf(-gs[s], ys[s * Cp + c], a0);
-        a1 = fmaf(-gs[s + 1], ys[(s + 1) * Cp + c], a1);
+      if (soft) {
+        int s = 0;
+        for (; s + 1 < Lb; s += 2) {
+          a0 = fmaf(-gs[s], S.ys[s * Cp + c], a0);
+          a1 = fmaf(-gs[s + 1], S.ys[(s + 1) * Cp + c], a1);
+        }
+        if (s < Lb) a0 = fmaf(-gs[s], S.ys[s * Cp + c], a0);
+      } else {
+        for (int wd = 0; wd < LW; ++wd) {
+          unsigned m = S.cmask[c * LW + wd];
+          while (m) {
+            a1 -= gs[wd * 32 + __ffs(m) - 1];
+            m &= m - 1;
+          }
+        }
       }
-      if (s < Lb) a0 = fmaf(-gs[s], ys[s * Cp + c], a0);
       g[c] = wgt * (a0 + a1);
     }
     __syncwarp();
@@ -374,8 +433,8 @@ int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cud
   const unsigned row_blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
   // binary variant: the sequence's multi-hot rows are cached in shared memory when they fit
   const int Cp = (int)(p.C | 1);
-  const size_t bin_smem_rs = sizeof(float) * ((size_t)p.Lmax * Cp + (size_t)kRowWarps * p.C);
-  const size_t bin_smem_gr = sizeof(float) * ((size_t)p.Lmax * Cp + (size_t)kRowWarps * p.Lmax);
+  const size_t bin_smem_rs = sizeof(float) * bin_smem_floats(p.Lmax, p.C, Cp, p.C);
+  const size_t bin_smem_gr = sizeof(float) * bin_smem_floats(p.Lmax, p.C, Cp, p.Lmax);
   const bool bin_smem = binary && std::max(bin_smem_rs, bin_smem_gr) <= 200 * 1024;
   const dim3 bin_grid((unsigned)p.B, (unsigned)((p.T + kBinTCh - 1) / kBinTCh));
   if (bin_smem) {
