@@ -86,6 +86,7 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
     c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
     c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * PSEQ);
     c.o_s2 = take(sizeof(double) * 2 * gb);
+    c.o_pub = take(16 * (size_t)gb);
     c.o_ab = take(sizeof(double) * 2 * (size_t)gb * ABSEQ);
     off = align_up(off, 128);
     c.o_ring = take((size_t)kNSlot * c.TT * c.RSg);

@@ -46,7 +46,7 @@ struct StreamCfg {
   int NTmax;  // ceil(T / TT)
   int ckpt_global;
   int ctas_per_sm;
-  uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_ab, o_ring, smem_bytes;
+  uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_pub, o_ab, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
   int* ws_cke;      // [B][NTmax]
   long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [160][32][2] trace
@@ -63,8 +63,12 @@ struct Geo {
   static constexpr int AS = Lpad + 8;          // alpha/beta tile row stride (doubles)
   static constexpr int PSEQ = TT * PS + 8;     // p-tile floats per sequence (+8: lane groups hit distinct banks)
   static constexpr int ABSEQ = 2 * TT * AS + 8;  // alpha+beta tile doubles per sequence
+  static constexpr int W = NS > 2 ? 32 : 16;   // chain lanes per direction (NS = Lpad/16 names the instance)
+  static constexpr int CNS = Lpad / W;         // chain states per lane
+  static constexpr int NCW = W == 32 ? 2 : 1;  // chain warps per sequence: W = 32 -> one for alpha, one for beta
+  static constexpr int NCHAIN = GB * NCW;
   static constexpr int NMW = 2;              // mover warps: TMA issue for TT/NMW time steps each
-  static constexpr int NTHREADS = 32 * (GB + NRW + NMW);
+  static constexpr int NTHREADS = 32 * (NCHAIN + NRW + NMW);
 };
 
 int launch_stream_ns2(const Problem& p, const StreamCfg& cfg, cudaStream_t stream);
@@ -181,6 +185,12 @@ __device__ __forceinline__ double pow2i(int e) {  // exact 2^e, e clamped to the
 #define PROF_DUMP(role_)
 #endif
 
+// what the alpha warp of a sequence publishes for its beta warp (two chain warps per sequence, W = 32)
+struct ChainPub {
+  double zinv;
+  int Ez, Eb;
+};
+
 struct Smem {
   uint64_t* sfull;  // [kNSlot][TT] "this time step's slab has landed" barriers
   int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags, [3*kMaxGB..) largest duplicate rank
@@ -189,20 +199,26 @@ struct Smem {
   int* cke;         // [GB][NTmax]
   float* ptile;     // [2][GB][PSEQ]
   double* s2;       // [2][GB]
+  ChainPub* pub;    // [GB] alpha warp -> beta warp hand-over (W = 32)
   double* ab;       // [2][GB][ABSEQ]
   unsigned char* ring;  // [kNSlot][TT][RSg]
 };
 
-// ============================================================================ chain warp
-// rescale the NS states of each 16-lane half by the exact power of two of the half's largest value
-template <int NS>
-__device__ __forceinline__ int rescale_half(double (&v)[NS]) {
+// ============================================================================ chain warps
+// W = 16: one warp per sequence; lanes 0-15 run alpha, lanes 16-31 run beta (phase 2) in the same instructions.
+// W = 32 (Lmax > 32): two warps per sequence, 32 lanes each: one runs alpha (phase 1 + replay), the other beta.
+// In both layouts position q of a direction's W lanes x NS states is state q for alpha and state Lpad-1-q for beta,
+// so both shift the same way.
+
+// rescale the NS states of each group of W lanes by the exact power of two of the group's largest value
+template <int NS, int W>
+__device__ __forceinline__ int rescale_group(double (&v)[NS]) {
   double m = v[0];
 #pragma unroll
   for (int j = 1; j < NS; ++j) m = fmax(m, v[j]);
   int hi = __double2hiint(m);  // values are >= 0, so the high word orders like the value
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  for (int o = W / 2; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   const int ex = hi >> 20;
   if (ex == 0 || ex >= 0x7ff) return 0;
   const int e = ex - 1023;
@@ -212,11 +228,10 @@ __device__ __forceinline__ int rescale_half(double (&v)[NS]) {
   return e;
 }
 
-// emissions of the lane's NS states for one row of a p-tile, in the lane's own state order: the beta half
-// (rev) holds state Lpad-1-q at position q
-template <int NS>
+// emissions of the lane's NS states for one row of a p-tile, in the lane's own state order (rev: beta)
+template <int NS, int W>
 __device__ __forceinline__ void load_p(const float* row, int hl, bool rev, double (&p)[NS]) {
-  const float* src = row + (rev ? (16 - 1 - hl) * NS : hl * NS);
+  const float* src = row + (rev ? (W - 1 - hl) * NS : hl * NS);
   float t[NS];
   if constexpr (NS == 2) {
     const float2 v = *reinterpret_cast<const float2*>(src);
@@ -235,16 +250,16 @@ __device__ __forceinline__ void load_p(const float* row, int hl, bool rev, doubl
 // x(s) <- (x(s) + x(s-1)) * p(s) in the lane's (possibly reversed) state order, written as
 // x(s) <- fma(x(s-1), p(s), x(s)*p(s)): the products x(s)*p(s) do not wait for the neighbour lane's state, so the
 // dependent path of a step is one shuffle + one DFMA for the lane's first state and one DFMA for the others
-// (a shuffle, a DADD and a DMUL in the textbook form).  alpha: x = alpha (NoBlankCTC.py:73-85).  beta half:
+// (a shuffle, a DADD and a DMUL in the textbook form).  alpha: x = alpha (NoBlankCTC.py:73-85).  beta:
 // x(s) = beta_t(s) p_t(s) and, with kSum, sum(s) = x(s) + x(s-1) = beta_t(s) (off the dependent path).
-// kFirst: first step of a tile -- `carry` enters position 0 of the half (the virtual start state:
+// kFirst: first step of a tile -- `carry` enters position 0 of the direction (the virtual start state:
 // NoBlankCTC.py:92-93 and the t>0 guard at :75); in every other step position 0 of lane 0 has no neighbour.
-template <int NS, bool kSum, bool kFirst>
+template <int NS, int W, bool kSum, bool kFirst>
 __device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry) {
   double t[NS];
 #pragma unroll
   for (int j = 0; j < NS; ++j) t[j] = x[j] * p[j];
-  double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
+  double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, W);
   double p0 = p[0];
   if (kFirst) {
     if (hl == 0) up = carry;
@@ -261,11 +276,11 @@ __device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], c
   x[0] = fma(up, p0, t[0]);
 }
 // run-time `first` (generic loops)
-template <int NS, bool kSum>
+template <int NS, int W, bool kSum>
 __device__ __forceinline__ void chain_step_rt(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry,
                                               bool first) {
-  if (first) chain_step<NS, kSum, true>(x, sum, p, hl, carry);
-  else chain_step<NS, kSum, false>(x, sum, p, hl, 0.0);
+  if (first) chain_step<NS, W, kSum, true>(x, sum, p, hl, carry);
+  else chain_step<NS, W, kSum, false>(x, sum, p, hl, 0.0);
 }
 
 // Chain-warp state lives in plain registers of the kernel body (passed by reference to force-inlined functions).
@@ -274,47 +289,59 @@ struct ChainScal {
   int Ea, Eb, Ez;
 };
 
-// ---- phase 1, tile k: alpha over the tile's steps (lanes 16-31 carry zeros)
-template <int NS, int TT, int PS>
+// ---- phase 1, tile k: alpha over the tile's steps (W = 16: lanes 16-31 carry zeros)
+template <int NS, int W, int TT, int PS>
 __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int lane, int Tb, double* ck, int* cke, int k,
                                              const float* __restrict__ pt) {
-  const int hl = lane & 15;
+  const int hl = lane & (W - 1);
   double sum[NS];
   if (k > 0) {
-    c.Ea += rescale_half<NS>(x);
-    if (lane < 16) {
+    c.Ea += rescale_group<NS, W>(x);
+    if (lane < W) {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) ck[(k * NS + j) * 16] = x[j];
+      for (int j = 0; j < NS; ++j) ck[(k * NS + j) * W] = x[j];
       if (lane == 0) cke[k] = c.Ea;
     }
   }
   const int nv = min(TT, Tb - k * TT);
-  if (NS <= 4 && nv == TT) {
+  if (NS <= 2 && nv == TT) {
     // whole tile of emissions in registers ahead of the dependent loop
     double pr[TT][NS];
 #pragma unroll
-    for (int i = 0; i < TT; ++i) load_p<NS>(pt + i * PS, hl, false, pr[i]);
+    for (int i = 0; i < TT; ++i) load_p<NS, W>(pt + i * PS, hl, false, pr[i]);
 #pragma unroll
     for (int i = 0; i < TT; ++i) {
-      if (i == 0) chain_step<NS, false, true>(x, sum, pr[i], hl, c.carry);
-      else chain_step<NS, false, false>(x, sum, pr[i], hl, 0.0);
+      if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry);
+      else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0);
     }
   } else {
 #pragma unroll 2
     for (int i = 0; i < nv; ++i) {
       double pf[NS];
-      load_p<NS>(pt + i * PS, hl, false, pf);
-      chain_step_rt<NS, false>(x, sum, pf, hl, c.carry, i == 0);
+      load_p<NS, W>(pt + i * PS, hl, false, pf);
+      chain_step_rt<NS, W, false>(x, sum, pf, hl, c.carry, i == 0);
     }
   }
   c.carry = 0.0;
 }
 
-// ---- read-out after the sequence's last phase-1 tile (NoBlankCTC.py:58-68,:139) + beta start state
-template <int NS>
-__device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int lane, int Lb, float* loss_out, float wgt) {
-  constexpr int Lpad = 16 * NS;
-  const int hl = lane & 15;
+// beta start state: position q holds state Lpad-1-q; x = u_t(s) = beta_t(s) p_t(s).  Virtual start
+// u_{T_b}(L_b) = 1 gives beta_{T_b-1}(L_b-1) = 1 without a branch (state L_b has p = 0 and alpha = 0).
+template <int NS, int W>
+__device__ __forceinline__ void chain_beta_init(double (&x)[NS], ChainScal& c, int hl, int Lb) {
+  constexpr int Lpad = W * NS;
+  c.Eb = 0;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) x[j] = (Lpad - 1 - (hl * NS + j) == Lb) ? 1.0 : 0.0;
+  c.carry = (hl == 0 && Lb == Lpad) ? 1.0 : 0.0;
+}
+
+// ---- read-out after the sequence's last phase-1 tile (NoBlankCTC.py:58-68,:139).  W = 16: the beta half of the
+// warp starts here; W = 32: the alpha warp publishes 1/Z and its exponent for the beta warp.
+template <int NS, int W>
+__device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int lane, int Lb, float* loss_out, float wgt,
+                                              ChainPub* pub) {
+  const int hl = lane & (W - 1);
   const int sl = Lb - 1;
   // x[sl % NS] without a dynamic index (which would push the state array into local memory)
   const int rj = sl % NS;
@@ -325,31 +352,30 @@ __device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int
   c.Ez = __shfl_sync(0xffffffffu, c.Ea, 0);
   if (lane == 0) *loss_out = (zhat > 0.0) ? (float)(-(log(zhat) + (double)c.Ez * 0.6931471805599453)) : INFINITY;
   c.zinv = (zhat > 0.0) ? (double)wgt / zhat : 0.0;  // sequence weight folded into gamma
-  // beta half: position q of the half holds state Lpad-1-q; x = u_t(s) = beta_t(s) p_t(s).  Virtual start
-  // u_{T_b}(L_b) = 1 gives beta_{T_b-1}(L_b-1) = 1 without a branch (state L_b has p = 0 and alpha = 0).
-  c.Eb = 0;
-  if (lane >= 16) {
-#pragma unroll
-    for (int j = 0; j < NS; ++j) x[j] = (Lpad - 1 - (hl * NS + j) == Lb) ? 1.0 : 0.0;
-    c.carry = (hl == 0 && Lb == Lpad) ? 1.0 : 0.0;
+  if (W == 16) {
+    if (lane >= 16) chain_beta_init<NS, W>(x, c, hl, Lb);
+    else c.Eb = 0;
+  } else if (lane == 0) {
+    pub->zinv = c.zinv;
+    pub->Ez = c.Ez;
+    pub->Eb = 0;
   }
 }
 
-// ---- phase 2, tile k: beta (lanes 16-31) + alpha replay (lanes 0-15) from the checkpoint (ckv, exponent EaK;
-// unused for k = 0); alpha_t(s), beta_t(s) -> ab tile
-template <int NS, int TT, int PS, int AS>
-__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, int Tb, const double (&ckv)[NS], int EaK,
-                                             int k, const float* __restrict__ pt, double* __restrict__ abt, double* s2_out) {
-  constexpr int Lpad = 16 * NS;
-  const int hl = lane & 15;
-  const bool isb = lane >= 16;
+// ---- phase 2, tile k: beta (isb) / alpha replay (!isb) from the checkpoint (ckv, exponent EaK; unused for
+// k = 0); alpha_t(s), beta_t(s) -> ab tile.  Eb_all: the beta direction's accumulated exponent.
+template <int NS, int W, int TT, int PS, int AS>
+__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, bool isb, int Eb_all, int Tb,
+                                             const double (&ckv)[NS], int EaK, int k, const float* __restrict__ pt,
+                                             double* __restrict__ abt, double* s2_out) {
+  constexpr int Lpad = W * NS;
+  const int hl = lane & (W - 1);
   double sum[NS];
   // gamma = alpha * beta * w / Z; the power-of-two part is split over both factors (range safety)
-  const int Eb_all = __shfl_sync(0xffffffffu, c.Eb, 16);
   const int d = EaK + Eb_all - c.Ez;
   const double s1 = pow2i(d / 2);
   const double s2 = -(pow2i(d - d / 2) * c.zinv);  // negative: the row warps ADD gamma' = -w*gamma to the softmax row
-  if (lane == 0) *s2_out = s2;
+  if (lane == 0 && !isb) *s2_out = s2;
   if (!isb) {
     if (k == 0) {
 #pragma unroll
@@ -365,15 +391,15 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
   const int sdir = isb ? -1 : 1;
   double* dst = abt + (isb ? TT * AS : 0) + s0;  // alpha tile, then beta tile
-  if (NS <= 4 && nv == TT) {
+  if (NS <= 2 && nv == TT) {
     double pr[TT][NS];
 #pragma unroll
-    for (int jj = 0; jj < TT; ++jj) load_p<NS>(pt + (isb ? TT - 1 - jj : jj) * PS, hl, isb, pr[jj]);
+    for (int jj = 0; jj < TT; ++jj) load_p<NS, W>(pt + (isb ? TT - 1 - jj : jj) * PS, hl, isb, pr[jj]);
 #pragma unroll
     for (int jj = 0; jj < TT; ++jj) {
       const int i = isb ? (TT - 1 - jj) : jj;  // alpha walks up the tile, beta walks down
-      if (jj == 0) chain_step<NS, true, true>(x, sum, pr[jj], hl, c.carry);
-      else chain_step<NS, true, false>(x, sum, pr[jj], hl, 0.0);
+      if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry);
+      else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0);
 #pragma unroll
       for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
     }
@@ -382,15 +408,15 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
     for (int jj = 0; jj < nv; ++jj) {
       const int i = isb ? (nv - 1 - jj) : jj;
       double pf[NS];
-      load_p<NS>(pt + i * PS, hl, isb, pf);
-      chain_step_rt<NS, true>(x, sum, pf, hl, c.carry, jj == 0);
+      load_p<NS, W>(pt + i * PS, hl, isb, pf);
+      chain_step_rt<NS, W, true>(x, sum, pf, hl, c.carry, jj == 0);
 #pragma unroll
       for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
     }
   }
   c.carry = 0.0;
-  // every lane takes part in the half-wide shuffles; only the beta half keeps the result
-  const int e = rescale_half<NS>(x);
+  // every lane takes part in the group-wide shuffles; only the beta direction keeps the result
+  const int e = rescale_group<NS, W>(x);
   if (isb) c.Eb += e;
 }
 
@@ -726,6 +752,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
   S.cke = reinterpret_cast<int*>(smem_raw + cfg.o_cke);
   S.ptile = reinterpret_cast<float*>(smem_raw + cfg.o_ptile);
   S.s2 = reinterpret_cast<double*>(smem_raw + cfg.o_s2);
+  S.pub = reinterpret_cast<ChainPub*>(smem_raw + cfg.o_pub);
   S.ab = reinterpret_cast<double*>(smem_raw + cfg.o_ab);
   S.ring = smem_raw + cfg.o_ring;
 
@@ -812,61 +839,76 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
 #define NBCTC_ITER_END() __syncthreads();
 #endif
 
-  if (warp < GB) {
-    // ======================================================================== chain warp of sequence `warp`
-    const int seq = warp;
+  if (warp < G::NCHAIN) {
+    // ======================================================================== chain warp(s) of sequence `seq`
+    constexpr int W = G::W, CNS = G::CNS, NCW = G::NCW;
+    const int seq = warp / NCW;
+    const bool beta_warp = NCW == 2 && (warp % NCW) == 1;  // W = 32: this warp runs beta only
+    const bool isb = NCW == 2 ? beta_warp : lane >= 16;
     const int Tb = S.info[seq], Lb = S.info[kMaxGB + seq];
     const int NTb = (Tb + TT - 1) / TT;
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     double* ck = (cfg.ckpt_global ? cfg.ws_ckpt + ((size_t)min(b0 + seq, P.B - 1) * cfg.NTmax) * Lpad
-                                  : S.ckpt + ((size_t)seq * cfg.NTmax) * Lpad) + (lane & 15);  // [NTmax][NS][16]
+                                  : S.ckpt + ((size_t)seq * cfg.NTmax) * Lpad) + (lane & (W - 1));  // [NTmax][CNS][W]
     int* cke = cfg.ckpt_global ? cfg.ws_cke + (size_t)min(b0 + seq, P.B - 1) * cfg.NTmax : S.cke + (size_t)seq * cfg.NTmax;
+    ChainPub* pub = S.pub + seq;
     ChainScal chain;
-    double cx[NS];
+    double cx[CNS];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) cx[j] = 0.0;
+    for (int j = 0; j < CNS; ++j) cx[j] = 0.0;
     chain.carry = (lane == 0) ? 1.0 : 0.0;
     chain.zinv = 0.0;
     chain.Ea = 0; chain.Eb = 0; chain.Ez = 0;
     // ---- phase 1
     for (int it = -1; it < NTg; ++it) {
-      if (it >= 0 && it < NTb) {
+      if (!beta_warp && it >= 0 && it < NTb) {
         const float* pt = S.ptile + (size_t)((it & 1) * GB + seq) * G::PSEQ;
-        PROF_SCOPE(0, chain_phase1<NS, TT, PS>(cx, chain, lane, Tb, ck, cke, it, pt))
+        PROF_SCOPE(0, chain_phase1<CNS, W, TT, PS>(cx, chain, lane, Tb, ck, cke, it, pt))
         // the gradient weight of a sequence with w = 0 is applied at the end of the kernel (see below)
-        if (it == NTb - 1) chain_readout<NS>(cx, chain, lane, Lb, &P.loss[b0 + seq], wgt);
+        if (it == NTb - 1) chain_readout<CNS, W>(cx, chain, lane, Lb, &P.loss[b0 + seq], wgt, pub);
       }
       NBCTC_ITER_END()
     }
     // ---- phase 2: item i = tile NTg-1-i
     if (want_grad) {
-      double ckv[NS];
+      double ckv[CNS];
       int EaK = 0;
       auto fetch_ckpt = [&](int k) {  // checkpoint of tile k (k = 0 starts from the virtual state instead)
         if (k > 0 && k < NTb) {
+          if (!beta_warp) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) ckv[j] = ck[(k * NS + j) * 16];
+            for (int j = 0; j < CNS; ++j) ckv[j] = ck[(k * CNS + j) * W];
+          }
           EaK = cke[k];
         } else {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) ckv[j] = 0.0;
+          for (int j = 0; j < CNS; ++j) ckv[j] = 0.0;
           EaK = 0;
         }
       };
+#pragma unroll
+      for (int j = 0; j < CNS; ++j) ckv[j] = 0.0;
       fetch_ckpt(NTg - 1);
       for (int i = -1; i <= NTg + 1; ++i) {
         if (i >= 0 && i < NTg) {
           const int k = NTg - 1 - i;
           if (k < NTb) {
-            double ckc[NS];
+            if (beta_warp && k == NTb - 1) {  // first tile of this sequence: take over from the alpha warp
+              chain.zinv = pub->zinv;
+              chain.Ez = pub->Ez;
+              chain_beta_init<CNS, W>(cx, chain, lane, Lb);
+            }
+            double ckc[CNS];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) ckc[j] = ckv[j];
+            for (int j = 0; j < CNS; ++j) ckc[j] = ckv[j];
             const int EaC = EaK;
             fetch_ckpt(k - 1);  // in flight while this tile runs
             const int buf = i & 1;
-            PROF_SCOPE(1, chain_phase2<NS, TT, PS, AS>(cx, chain, lane, Tb, ckc, EaC, k,
-                                                       S.ptile + (size_t)(buf * GB + seq) * G::PSEQ,
-                                                       S.ab + (size_t)(buf * GB + seq) * G::ABSEQ, &S.s2[buf * GB + seq]))
+            const int Eb_all = NCW == 2 ? (beta_warp ? chain.Eb : pub->Eb) : __shfl_sync(0xffffffffu, chain.Eb, 16);
+            PROF_SCOPE(1, chain_phase2<CNS, W, TT, PS, AS>(cx, chain, lane, isb, Eb_all, Tb, ckc, EaC, k,
+                                                           S.ptile + (size_t)(buf * GB + seq) * G::PSEQ,
+                                                           S.ab + (size_t)(buf * GB + seq) * G::ABSEQ, &S.s2[buf * GB + seq]))
+            if (beta_warp && lane == 0) pub->Eb = chain.Eb;  // read by the alpha warp after the barrier
           } else {
             fetch_ckpt(k - 1);
           }
@@ -875,9 +917,9 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
       }
     }
     PROF_DUMP(0)
-  } else if (warp < GB + G::NRW) {
+  } else if (warp < G::NCHAIN + G::NRW) {
     // ======================================================================== row warp of time step `ti`
-    const int ti = warp - GB;
+    const int ti = warp - G::NCHAIN;
     const int seq = lane / LPR;
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     const Rows<NS, LPR, CPL> rows(P, cfg, S, lane, ti, gcnt, b0, wgt);
@@ -932,7 +974,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     // once (evict_first); the phase-1 gradient rows must survive in L2 until phase 2 (evict_last); phase 2 reads
     // and rewrites them for the last time (evict_first).
     constexpr int PER = TT / G::NMW;
-    const int ti = (warp - GB - G::NRW) * PER + lane;
+    const int ti = (warp - G::NCHAIN - G::NRW) * PER + lane;
     const bool mine = lane < PER;
     const Rows<NS, LPR, CPL> mv(P, cfg, S, lane, mine ? ti : 0, gcnt, b0, 0.f);
     const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
