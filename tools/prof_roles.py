@@ -17,9 +17,11 @@ from ctc_b200 import _ffi
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w = bench.WORKLOADS[name]
 B, T, Cc, Lmax = w["B"], w["T"], w["C"], w["Lmax"]
-LPR = int(os.environ.get("NBCTC_LPR", "8"))
+nch = Cc // 4 if Cc % 4 == 0 else (Cc + 6) // 4
+LPR = int(os.environ.get("NBCTC_LPR", "0")) or (4 if nch <= 16 else 8 if nch <= 64 else 32)
 GB = 32 // LPR
-NRW = 8
+NRW = 4 if Lmax > 128 else 8            # row warps = time steps per tile
+NCH = GB * (2 if Lmax > 32 else 1)      # chain warps
 dev = torch.device("cuda:0")
 tg, il, tl = bench.make_inputs_np(w, 1234)
 x = torch.randn((T, B, Cc), device=dev)
@@ -52,7 +54,7 @@ p = pall[:24].reshape(3, 8)
 trace = pall[24:].reshape(160, 32, 2)
 groups = (B + GB - 1) // GB
 names = {
-    0: ("chain", GB, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
+    0: ("chain", NCH, ["phase1 steps", "phase2 steps", "-", "-", "-", "-", "barrier", "total"]),
     1: ("row", NRW, ["wait rows", "forward step", "-", "-", "emit (ph2)", "scatter", "barrier", "total"]),
     2: ("mover", 2, ["store issue", "wait store reads", "load issue", "-", "-", "-", "barrier", "total"]),
 }
@@ -63,7 +65,7 @@ for role, (rn, nw, nm) in names.items():
     print(f"  {rn:9s} " + "  ".join(f"{n}={v:,.0f}" for n, v in zip(nm, m) if n != "-"))
 
 # per-iteration trace of the middle CTA: cycles each role spends working in the iteration (work end - previous barrier end)
-nw = GB + NRW + 2
+nw = NCH + NRW + 2
 prev = np.zeros(nw)
 print("trace of one CTA: iteration | iteration cycles | busy cycles chain(max) rows(max)")
 for itx in range(160):
@@ -71,5 +73,5 @@ for itx in range(160):
         break
     busy = trace[itx, :nw, 0] - prev
     end = trace[itx, :nw, 1]
-    print(f"  it={itx:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:GB].max():6.0f} rows={busy[GB:GB + NRW].max():6.0f} movers={busy[GB + NRW:].max():6.0f}")
+    print(f"  it={itx:3d} iter={end.max() - prev.max():7.0f}  chain={busy[:NCH].max():6.0f} rows={busy[NCH:NCH + NRW].max():6.0f} movers={busy[NCH + NRW:].max():6.0f}")
     prev = end
