@@ -14,6 +14,7 @@ OK = 0
 FLAG_DEFAULT = 0
 FLAG_GENERIC = 1
 FLAG_NO_GRAD = 2
+FLAG_ALIGNED16 = 4
 
 _lib = None
 

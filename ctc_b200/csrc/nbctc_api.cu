@@ -64,7 +64,12 @@ int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void
 int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t stream) {
   if (flags & NBCTC_FLAG_NO_GRAD) p.grad = nullptr;
   int rc;
-  const bool use_fused = !(flags & NBCTC_FLAG_GENERIC) && fused_supported(p.T, p.B, p.C, p.Lmax, binary) && fused_pointers_ok(p);
+  const bool shape_ok = !(flags & NBCTC_FLAG_GENERIC) && fused_supported(p.T, p.B, p.C, p.Lmax, binary);
+  if (shape_ok && (flags & NBCTC_FLAG_ALIGNED16) && !fused_pointers_ok(p)) {
+    set_error("NBCTC_FLAG_ALIGNED16 was passed but logits / grad_logits are not 16-byte aligned");
+    return NBCTC_ERR_INVALID_ARG;
+  }
+  const bool use_fused = shape_ok && fused_pointers_ok(p);
   if (use_fused)
     rc = fused_launch(p, binary, ws, ws_bytes, stream);
   else
@@ -158,7 +163,10 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   size_t g = generic_workspace_bytes(T, B, C, Lmax);
   if (flags & NBCTC_FLAG_GENERIC) return g;
   // the generic size is kept as a floor: a call with 16-byte misaligned tensors falls back to that path
-  if (fused_supported(T, B, C, Lmax, binary != 0)) return std::max(g, fused_workspace_bytes(T, B, C, Lmax, binary != 0));
+  if (fused_supported(T, B, C, Lmax, binary != 0)) {
+    const size_t f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
+    return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
+  }
   return g;
 }
 

@@ -39,6 +39,8 @@ def _launch(x, targets, in_len, tgt_len, binary, want_grad, w_scalar, seq_w, fla
     grad = torch.empty_like(x) if want_grad else None
     if not want_grad:
         flags |= _ffi.FLAG_NO_GRAD
+    if x.data_ptr() % 16 == 0 and (grad is None or grad.data_ptr() % 16 == 0):
+        flags |= _ffi.FLAG_ALIGNED16    # no workspace for the unaligned-tensor fallback (torch allocations are aligned)
     ws_bytes = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 1 if binary else 0, flags))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     fn = lib.nbbctc_loss_grad_f32 if binary else lib.nbctc_loss_grad_f32

@@ -45,6 +45,9 @@ extern "C" {
 #define NBCTC_FLAG_DEFAULT 0u
 #define NBCTC_FLAG_GENERIC 1u     /* force the unfused three-kernel path (debug / cross-check) */
 #define NBCTC_FLAG_NO_GRAD 2u     /* loss only (validate(), train.py:486,576 runs under no_grad) */
+#define NBCTC_FLAG_ALIGNED16 4u   /* caller guarantees 16-byte aligned logits and grad_logits: the workspace query
+                                     then omits the room for the unaligned-tensor fallback (the call fails with
+                                     NBCTC_ERR_INVALID_ARG if the promise is broken) */
 
 typedef void* nbctc_stream_t; /* cudaStream_t */
 

@@ -341,3 +341,25 @@ def test_slab_alignment_phases(nb, shape):
     x, lab, il, tl = make_ctc_case(500 + T + C, T, B, C, L, ragged_T=True, dup=True)
     loss, grad = run_cuda(nb, "ctc", x, lab, il, tl)
     assert_parity(loss, grad, oracle("ctc", x, lab, il, tl))
+
+
+def test_aligned16_flag_contract(nb):
+    """NBCTC_FLAG_ALIGNED16: smaller workspace query; a broken promise is an error, not a wrong answer."""
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    T, B, C, L = 64, 16, 157, 8
+    full = int(lib.nbctc_workspace_bytes(T, B, C, L, 0, 0))
+    lean = int(lib.nbctc_workspace_bytes(T, B, C, L, 0, _ffi.FLAG_ALIGNED16))
+    assert 0 < lean < full
+    x, lab, il, tl = make_ctc_case(5, T, B, C, L)
+    xs = torch.empty(x.size + 1, device=DEV)
+    xd = xs[1:].view(T, B, C)          # 4-byte offset: not 16-byte aligned
+    xd.copy_(torch.tensor(x))
+    per = torch.empty(B, device=DEV)
+    grad = torch.empty((T, B, C), device=DEV)
+    ws = torch.empty(full, dtype=torch.uint8, device=DEV)
+    args = (xd.data_ptr(), T, B, C, torch.tensor(lab, device=DEV).data_ptr(), L, torch.tensor(il, device=DEV).data_ptr(),
+            torch.tensor(tl, device=DEV).data_ptr(), per.data_ptr(), None, None, grad.data_ptr(), None, 1.0 / B,
+            ws.data_ptr(), full)
+    rc = lib.nbctc_loss_grad_f32(*args, _ffi.FLAG_ALIGNED16, torch.cuda.current_stream().cuda_stream)
+    assert rc == -1 and b"16-byte aligned" in lib.nbctc_last_error()
