@@ -627,7 +627,7 @@ struct Rows {
       const float m = group_max(m_l);
       const float cf = (m_l > kNegInf) ? ex2f((m_l - m) * kLog2e) : 0.f;  // this lane's exponentials -> row maximum
       const float s = group_sum(((s0 + s1) + (s2 + s3)) * cf);
-      const float sc = act ? weff * cf / s : 0.f;
+      const float sc = act ? __fdividef(weff * cf, s) : 0.f;  // 1 <= s <= C: the fast division is exact to 2 ulp
 #pragma unroll
       for (int c = 0; c < CPL; ++c) store_slot(g, c, scale4(v[c], sc));
     } else {
