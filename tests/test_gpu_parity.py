@@ -98,6 +98,8 @@ BCTC_SHAPES = [
     (60, 3, 157, 32, 0.5),
     (100, 2, 300, 70, 0.02),
     (257, 5, 157, 17, 0.03),
+    (20, 2, 400, 150, 0.02),              # multi-hot rows too large for shared memory: global-memory kernels
+    (300, 3, 64, 40, 0.05),               # several 128-step chunks per sequence
 ]
 
 
