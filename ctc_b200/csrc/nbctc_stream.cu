@@ -45,7 +45,7 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   StreamCfg& c = pl.cfg;
   c.NS = Lmax <= 32 ? 2 : Lmax <= 64 ? 4 : Lmax <= 128 ? 8 : 16;  // 16 chain lanes per direction
   c.Lpad = 16 * c.NS;
-  c.TT = c.NS >= 16 ? 4 : 8;
+  c.TT = c.NS >= 16 ? 2 : 8;
   const int PS = c.Lpad + 8, AS = c.Lpad + 8;
   const int PSEQ = c.TT * PS + 8, ABSEQ = 2 * c.TT * AS + 8;
   // chunks per row: with C % 4 == 0 every row starts on a 16-byte boundary, otherwise at any of the 4 phases

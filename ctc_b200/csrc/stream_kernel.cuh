@@ -54,7 +54,9 @@ struct StreamCfg {
 
 template <int NS, int LPR>
 struct Geo {
-  static constexpr int TT = NS >= 16 ? 4 : 8;  // time steps per tile
+  // time steps per tile.  Lpad = 256: two steps only, so that the tiles are small and three CTAs (one sequence
+  // each) share an SM -- these chains are long and the only parallelism is across sequences
+  static constexpr int TT = NS >= 16 ? 2 : 8;
   static constexpr int Lpad = 16 * NS;
   static constexpr int GB = 32 / LPR;          // sequences per CTA
   static constexpr int NRW = TT;               // row warps: one per time step of a tile
@@ -1046,9 +1048,11 @@ template <int NS, int LPR, int CPL>
 int launch_inst(const Problem& p, const StreamCfg& cfg, cudaStream_t stream) {
   using G = Geo<NS, LPR>;
   const unsigned groups = (unsigned)((p.B + G::GB - 1) / G::GB);
-  if constexpr (G::NTHREADS * 2 <= 1024) {
-    if (cfg.ctas_per_sm >= 2) {
-      auto kern = nbctc_stream_kernel<NS, LPR, CPL, 2>;
+  // registers: MINB = CTAs that should share an SM (3 for the small-tile Lpad = 256 geometry, NBCTC_CTAS otherwise)
+  constexpr int kWant = NS >= 16 ? 3 : 2;
+  if constexpr (G::NTHREADS * kWant <= 1024) {
+    if (cfg.ctas_per_sm >= 2 || NS >= 16) {
+      auto kern = nbctc_stream_kernel<NS, LPR, CPL, kWant>;
       if (cfg.smem_bytes > 48 * 1024)
         NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes));
       NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
