@@ -306,7 +306,7 @@ __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int 
     }
   }
   const int nv = min(TT, Tb - k * TT);
-  if (NS <= 2 && nv == TT) {
+  if (NS * TT <= 16 && nv == TT) {
     // whole tile of emissions in registers ahead of the dependent loop
     double pr[TT][NS];
 #pragma unroll
@@ -393,7 +393,7 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
   const int sdir = isb ? -1 : 1;
   double* dst = abt + (isb ? TT * AS : 0) + s0;  // alpha tile, then beta tile
-  if (NS <= 2 && nv == TT) {
+  if (NS * TT <= 16 && nv == TT) {
     double pr[TT][NS];
 #pragma unroll
     for (int jj = 0; jj < TT; ++jj) load_p<NS, W>(pt + (isb ? TT - 1 - jj : jj) * PS, hl, isb, pr[jj]);
