@@ -20,7 +20,7 @@ B, T, Cc, Lmax = w["B"], w["T"], w["C"], w["Lmax"]
 nch = Cc // 4 if Cc % 4 == 0 else (Cc + 6) // 4
 LPR = int(os.environ.get("NBCTC_LPR", "0")) or (4 if nch <= 16 else 8 if nch <= 64 else 32)
 GB = 32 // LPR
-NRW = 4 if Lmax > 128 else 8            # row warps = time steps per tile
+NRW = 2 if Lmax > 128 else 8            # row warps = time steps per tile
 NCH = GB * (2 if Lmax > 32 else 1)      # chain warps
 dev = torch.device("cuda:0")
 tg, il, tl = bench.make_inputs_np(w, 1234)
