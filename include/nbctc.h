@@ -131,6 +131,40 @@ int nbctc_best_path_i32(const float* logits, int64_t T, int64_t B, int64_t C,
 size_t nbctc_best_path_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 
 /*
+ * Evaluation metrics of the reference's training loop; integer results, ties in the
+ * top-k go to the LOWER class index (torch.topk leaves the order of ties open), NaN scores rank first.
+ *
+ * nbctc_frame_topk_i32: top-K classes of every score row, best first (`output.topk(maxk, 1, True, True)`,
+ * train.py:48,65,90,118).  Row (o, i), o < n_outer, i < n_inner, starts at scores + o*stride_outer +
+ * i*stride_inner (strides in elements; the C scores of a row are contiguous); pred is (n_outer, n_inner, K)
+ * int32, -1 where K > C.  1 <= K <= 8.  For `output[b]` slices of a (T,B,C) tensor: n_outer = B,
+ * n_inner = T, stride_outer = C, stride_inner = B*C.
+ */
+int nbctc_frame_topk_i32(const float* scores, int64_t n_outer, int64_t n_inner, int64_t stride_outer,
+                         int64_t stride_inner, int64_t C, int K, int32_t* pred, nbctc_stream_t stream);
+
+/*
+ * Greedy monotone matching of per-frame predictions against a multi-hot transcript, for B samples at once.
+ *   pred (B, frames, K) int32 from nbctc_frame_topk_i32; target (B, Lt, C) float multi-hot (> 0.5 = set);
+ *   time (B) int32 = the `time` / `trans` argument per sample (rows of target in use; NULL = Lt).
+ *   mode 0 = accuracy_time (train.py:111-136): correct is (B, K, frames), flag per frame;
+ *   mode 1 = recall_time   (train.py:82-107):  correct is (B, K, Lt), flag per transcript row; as in the
+ *            reference only the first time[b] frames are scanned (train.py:96).
+ *   counts (B, K) int32 (nullable) = sum of the flags of each rank: the reference's res[k] is
+ *   100 * sum(counts[b, :k]) / frames (mode 0) or / time[b] (mode 1).
+ */
+int nbctc_match_time_i32(const int32_t* pred, const float* target, const int32_t* time, int64_t B,
+                         int64_t frames, int K, int64_t Lt, int64_t C, int mode, int32_t* correct,
+                         int32_t* counts, nbctc_stream_t stream);
+
+/*
+ * Per-sample hit flags: accuracy_s (train.py:41-56; label (B) int32 class index, target NULL) or accuracy
+ * (train.py:59-78; target (B, C) float multi-hot, label NULL).  pred (B, K); correct (K, B) int32.
+ */
+int nbctc_match_frame_i32(const int32_t* pred, const int32_t* label, const float* target, int64_t B, int K,
+                          int64_t C, int32_t* correct, nbctc_stream_t stream);
+
+/*
  * Host-buffer convenience entry points (every pointer is a HOST pointer): copy in,
  * run on `device`, copy the loss (and the gradient when grad_logits_host != NULL) back,
  * synchronise.  For non-PyTorch hosts and for end-to-end timing.
