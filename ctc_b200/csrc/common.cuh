@@ -54,7 +54,14 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // generic (unfused) path
 size_t generic_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
-int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream);
+// gate: null, or a device flag -- the kernels run only if *gate != 0 (fallback of the tiled multi-label path)
+int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream, const int* gate = nullptr);
+
+// tiled path of the multi-label variant (nbctc_bin.cu): exact {0,1} targets with <= 31 classes per state; anything
+// else is detected on the device and handed to the gated generic kernels through *flag_out
+bool tiled_bin_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+size_t tiled_bin_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream, const int** flag_out);
 
 // fused path (single block-streaming kernel: row stream -> alpha, beta -> gradient; nbctc_stream.cu)
 bool fused_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax, bool binary);

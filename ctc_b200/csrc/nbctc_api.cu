@@ -70,10 +70,24 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
     return NBCTC_ERR_INVALID_ARG;
   }
   const bool use_fused = shape_ok && fused_pointers_ok(p);
-  if (use_fused)
+  if (use_fused) {
     rc = fused_launch(p, binary, ws, ws_bytes, stream);
-  else
+  } else if (binary && !(flags & NBCTC_FLAG_GENERIC) && tiled_bin_supported(p.T, p.B, p.C, p.Lmax)) {
+    // multi-label: whether the tiled kernels can take the call depends on the target VALUES (exact {0,1}, at most 31
+    // classes per state), which only the device sees: workspace = [generic | tiled]; the pre-pass sets a flag and
+    // either the tiled kernels or the gated generic kernels do the work
+    const size_t g = align_up(generic_workspace_bytes(p.T, p.B, p.C, p.Lmax), 256);
+    const size_t t = tiled_bin_workspace_bytes(p.T, p.B, p.C, p.Lmax);
+    if (ws == nullptr || ws_bytes < g + t) {
+      set_error("workspace too small: need %zu bytes, got %zu", g + t, ws_bytes);
+      return NBCTC_ERR_WORKSPACE;
+    }
+    const int* flag = nullptr;
+    rc = tiled_bin_launch(p, static_cast<char*>(ws) + g, t, stream, &flag);
+    if (rc == NBCTC_OK) rc = generic_launch(p, true, ws, g, stream, flag);
+  } else {
     rc = generic_launch(p, binary, ws, ws_bytes, stream);
+  }
   if (rc != NBCTC_OK) return rc;
   if (p.loss_sum || p.loss_reduced) rc = reduce_loss_launch(p, stream);
   return rc;
@@ -167,6 +181,7 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
     const size_t f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
     return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
   }
+  if (binary && tiled_bin_supported(T, B, C, Lmax)) return align_up(g, 256) + tiled_bin_workspace_bytes(T, B, C, Lmax);
   return g;
 }
 

@@ -22,6 +22,7 @@ struct GenericWs {
   float* emis;    // (T,B,Lmax) raw emission, overwritten by gamma
   double* alpha;  // (T,B,Lmax)
   int* bad;       // (B) label-out-of-range flag
+  const int* gate;  // null, or: run only if *gate != 0 (the fused binary kernel declined the call, nbctc_stream.cu)
 };
 
 __host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lmax) {
@@ -49,6 +50,7 @@ __host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lm
 template <bool kBinary>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rowstats_kernel(Problem p, GenericWs w) {
+  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (row >= p.T * p.B) return;
@@ -108,6 +110,7 @@ rowstats_kernel(Problem p, GenericWs w) {
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 lattice_kernel(Problem p, GenericWs w) {
+  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
   extern __shared__ double sm[];  // [2][Lmax]
   const int64_t b = blockIdx.x;
   const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
@@ -182,6 +185,7 @@ lattice_kernel(Problem p, GenericWs w) {
 template <bool kBinary>
 __global__ void __launch_bounds__(kRowWarps * 32)
 grad_kernel(Problem p, GenericWs w) {
+  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (row >= p.T * p.B) return;
@@ -272,6 +276,7 @@ __device__ __forceinline__ BinSmem bin_setup(const Problem& p, int64_t b, int Lb
 // emissions e[t,b,s] = (1/C) y_s . x_t and the row constant (1/C) sum_c softplus(x_c) (NoBlankBinaryCTC.py:109-112)
 __global__ void __launch_bounds__(kRowWarps * 32)
 rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
+  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
   extern __shared__ float smf[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
@@ -329,6 +334,7 @@ rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
 // grad[t,b,c] = w/C * (sigmoid(x) - sum_s gamma_t(s) y[b,s,c])
 __global__ void __launch_bounds__(kRowWarps * 32)
 grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
+  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
   extern __shared__ float smf[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
@@ -418,12 +424,13 @@ int reduce_loss_launch(const Problem& p, cudaStream_t stream) {
   return NBCTC_OK;
 }
 
-int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream) {
+int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaStream_t stream, const int* gate) {
   if (p.Lmax > 8192) {
     set_error("generic path supports Lmax <= 8192 (got %lld)", (long long)p.Lmax);
     return NBCTC_ERR_UNSUPPORTED;
   }
   GenericWs w;
+  w.gate = gate;
   size_t need = carve(&w, ws, p.T, p.B, p.Lmax);
   if (ws == nullptr || ws_bytes < need) {
     set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);

@@ -100,6 +100,10 @@ BCTC_SHAPES = [
     (257, 5, 157, 17, 0.03),
     (20, 2, 400, 150, 0.02),              # multi-hot rows too large for shared memory: global-memory kernels
     (300, 3, 64, 40, 0.05),               # several 128-step chunks per sequence
+    (50, 3, 100, 100, 0.03),              # tiled path, 8 chain states per lane
+    (37, 2, 64, 200, 0.05),               # tiled path, 16 chain states per lane
+    (130, 6, 256, 20, 0.02),              # tiled path, widest class dimension (byte class indices)
+    (24, 3, 7, 5, 0.3),                   # tiny class dimension
 ]
 
 
