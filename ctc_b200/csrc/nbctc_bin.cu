@@ -7,14 +7,14 @@
 //                      class -> states bit masks; raises a flag when a row is not exact {0,1} or holds more than
 //                      31 classes -- every kernel below then returns at once and the generic kernels (gated on the
 //                      same flag) run instead.
-//   K1 bin_emis      : CTA = one sequence x 128 time steps, warp = batches of 8 rows staged in shared memory;
+//   K1 bin_emis      : CTA = one sequence x 256 time steps, warp = batches of 8 rows staged in shared memory;
 //                      row constant (1/C) sum_c softplus(x_c) and emissions e_t(s) = (1/C) sum_{c in S_s} x_t(c)
 //                      with lane = state (NoBlankBinaryCTC.py:109-112: -BCELoss(sigmoid(x_t), y_s)).
 //   K2 lattice_tile  : warp = sequence; the float64 linear-domain chain of the fused kernel (stream_kernel.cuh:
 //                      16 lanes x NS states per direction, exact power-of-two rescaling, one alpha checkpoint per
 //                      tile of 8 steps, alpha replay next to beta in phase 2) on the emission tiles;
 //                      gamma overwrites the emissions (NoBlankBinaryCTC.py:72-95 transition, read-out :58-68).
-//   K3 bin_grad      : CTA = one sequence x 128 time steps, warp = batches of 8 rows, lane = class:
+//   K3 bin_grad      : CTA = one sequence x 256 time steps, warp = batches of 8 rows, lane = class:
 //                      grad = w/C * (sigmoid(x) - sum_{s in M_c} gamma_t(s)), the states of a class walked over its
 //                      bit mask once per batch (ascending state order: deterministic).
 //
@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kTB = 8;        // rows (time steps) per warp batch
 constexpr int kRowWarps = 8;  // warps per CTA in K1 / K3
-constexpr int kTCh = 128;     // time steps per CTA in K1 / K3
+constexpr int kTCh = 256;     // time steps per CTA in K1 / K3
 constexpr int kLatWarps = 4;  // sequences per CTA in K2
 
 struct TiledWs {
@@ -84,9 +84,15 @@ __global__ void __launch_bounds__(256) bin_prepass_kernel(Problem p, TiledWs w) 
     const int C = (int)p.C;
     int count = 0;
     bool bad = false;
-    for (int c0 = 0; c0 < C; c0 += 32) {
+    float yv[8];  // C <= 256: the whole row, loaded ahead of the ballots and atomics
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yv[i] = lane + 32 * i < C ? __ldg(y + lane + 32 * i) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c0 = 32 * i;
+      if (c0 >= C) break;
       const int c = c0 + lane;
-      const float v = c < C ? y[c] : 0.f;
+      const float v = yv[i];
       const bool one = v == 1.f;
       bad |= !(one || v == 0.f);
       const unsigned m = __ballot_sync(0xffffffffu, one);
@@ -110,8 +116,10 @@ __device__ __forceinline__ float softplus_fast(float v) {
 }
 
 // ------------------------------------------------------------------------------------ K1: emissions
-__global__ void __launch_bounds__(kRowWarps * 32) bin_emis_kernel(Problem p, TiledWs w, int Cp) {
+template <int NCI>
+__global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_kernel(Problem p, TiledWs w) {
   if (*w.flag != 0) return;
+  constexpr int Cp = 32 * NCI + 8;  // row stride: rows start 8 banks apart
   extern __shared__ float smf[];  // [kRowWarps][kTB][Cp]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
@@ -124,20 +132,32 @@ __global__ void __launch_bounds__(kRowWarps * 32) bin_emis_kernel(Problem p, Til
   const float invC = 1.f / (float)C;
   float* xs = smf + (size_t)warp * kTB * Cp;
   const int64_t rstride = p.B * p.C;  // floats between consecutive time steps of a sequence
-  for (int64_t tb0 = t0 + (int64_t)warp * kTB; tb0 < tend; tb0 += kRowWarps * kTB) {
+  // the whole batch of a warp is in flight before its first use: one memory round trip per batch.  (Requesting the
+  // next batch ahead of the walk keeps v live across it: 124 registers, two CTAs per SM, 0.34 instead of 0.26 ms.)
+  float v[NCI][kTB];
+  auto request = [&](int64_t tb0) {
     const int nrow = (int)min((int64_t)kTB, tend - tb0);
     const float* x0 = p.logits + (tb0 * p.B + b) * p.C;
+#pragma unroll
+    for (int i = 0; i < NCI; ++i) {
+      const int c = lane + 32 * i;
+#pragma unroll
+      for (int r = 0; r < kTB; ++r) v[i][r] = (c < C && r < nrow) ? __ldg(x0 + r * rstride + c) : 0.f;
+    }
+  };
+  for (int64_t tb0 = t0 + (int64_t)warp * kTB; tb0 < tend; tb0 += kRowWarps * kTB) {
+    const int nrow = (int)min((int64_t)kTB, tend - tb0);
+    request(tb0);
     float sp[kTB];
 #pragma unroll
     for (int r = 0; r < kTB; ++r) sp[r] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      float v[kTB];
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) v[r] = r < nrow ? __ldg(x0 + r * rstride + c) : 0.f;
+    for (int i = 0; i < NCI; ++i) {
+      const int c = lane + 32 * i;
 #pragma unroll
       for (int r = 0; r < kTB; ++r) {
-        xs[r * Cp + c] = v[r];
-        sp[r] += softplus_fast(v[r]);
+        xs[r * Cp + c] = v[i][r];
+        sp[r] += c < C ? softplus_fast(v[i][r]) : 0.f;
       }
     }
 #pragma unroll
@@ -189,8 +209,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) bin_emis_kernel(Problem p, Til
 }
 
 // ------------------------------------------------------------------------------------ K2: lattice on emission tiles
+// NS = 2: at most 72 registers, so that 28 warps share an SM (4096 sequences are then a single wave on 148 SMs)
 template <int NS>
-__global__ void __launch_bounds__(kLatWarps * 32) lattice_tile_kernel(Problem p, TiledWs w) {
+__global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_kernel(Problem p, TiledWs w) {
   if (*w.flag != 0) return;
   using namespace stream;
   constexpr int W = 16, TT = 8, Lpad = 16 * NS, PS = Lpad + 8, AS = Lpad + 8;
@@ -215,23 +236,33 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_tile_kernel(Problem p,
 
   // emission tile k -> registers (issued one tile ahead of its use), then -> p-tile in shared memory:
   // p_t(s) = exp(e_t(s) - rowc_t) <= 1 (floored like the fused kernel), 0 for states >= L_b and steps >= T_b
+  constexpr int NPR = Lpad / 32;  // floats per lane and tile row
+  const int64_t estride = p.B * (int64_t)Lmax;
+  float* const e_b = w.emis + b * Lmax + lane;
+  const float* const rc_b = w.rowc + b;
+  bool sv[NPR];
+#pragma unroll
+  for (int q = 0; q < NPR; ++q) sv[q] = lane + 32 * q < Lb;
   float ev[NPF], rcv = 0.f;
   auto fetch = [&](int k) {
-    const int64_t t0 = (int64_t)k * TT;
-    rcv = (lane < TT && t0 + lane < Tb) ? __ldg(w.rowc + (t0 + lane) * p.B + b) : 0.f;
+    const int t0 = k * TT, nv = min(TT, Tb - t0);
+    rcv = lane < nv ? __ldg(rc_b + (int64_t)(t0 + lane) * p.B) : 0.f;
+    const float* pe = e_b + (int64_t)t0 * estride;
 #pragma unroll
-    for (int i = 0; i < NPF; ++i) {
-      const int idx = lane + 32 * i, r = idx / Lpad, s = idx - r * Lpad;
-      ev[i] = (t0 + r < Tb && s < Lb) ? __ldg(w.emis + ((t0 + r) * p.B + b) * Lmax + s) : 0.f;
+    for (int r = 0; r < TT; ++r) {
+#pragma unroll
+      for (int q = 0; q < NPR; ++q) ev[r * NPR + q] = (r < nv && sv[q]) ? __ldg(pe + 32 * q) : 0.f;
+      pe += estride;
     }
   };
   auto stage = [&](int k) {
-    const int t0 = k * TT;
+    const int nv = min(TT, Tb - k * TT);
 #pragma unroll
-    for (int i = 0; i < NPF; ++i) {
-      const int idx = lane + 32 * i, r = idx / Lpad, s = idx - r * Lpad;
+    for (int r = 0; r < TT; ++r) {
       const float rc = __shfl_sync(0xffffffffu, rcv, r);
-      pt[r * PS + s] = (t0 + r < Tb && s < Lb) ? fmaxf(ex2f((ev[i] - rc) * kLog2e), kPMin) : 0.f;
+#pragma unroll
+      for (int q = 0; q < NPR; ++q)
+        pt[r * PS + lane + 32 * q] = (r < nv && sv[q]) ? fmaxf(ex2f((ev[r * NPR + q] - rc) * kLog2e), kPMin) : 0.f;
     }
   };
 
@@ -275,20 +306,24 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_tile_kernel(Problem p,
     __syncwarp();
     // gamma_t(s) = alpha_t(s) beta_t(s) / Z (s2 = -1/Z and the tile exponents) -> emission tile
     const double s2 = *s2p;
-    const int t0 = k * TT;
+    const int t0 = k * TT, nv = min(TT, Tb - t0);
+    float* pe = e_b + (int64_t)t0 * estride;
 #pragma unroll
-    for (int i = 0; i < NPF; ++i) {
-      const int idx = lane + 32 * i, r = idx / Lpad, s = idx - r * Lpad;
-      if (t0 + r < Tb && s < Lb)
-        w.emis[((int64_t)(t0 + r) * p.B + b) * Lmax + s] = -(float)(abt[r * AS + s] * (abt[(TT + r) * AS + s] * s2));
+    for (int r = 0; r < TT; ++r) {
+#pragma unroll
+      for (int q = 0; q < NPR; ++q) {
+        const int st = lane + 32 * q;
+        if (r < nv && sv[q]) pe[32 * q] = -(float)(abt[r * AS + st] * (abt[(TT + r) * AS + st] * s2));
+      }
+      pe += estride;
     }
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------ K3: gradient
-template <int NCI>
-__global__ void __launch_bounds__(kRowWarps * 32) bin_grad_kernel(Problem p, TiledWs w, int Lp) {
+template <int NCI, int Lp>
+__global__ void __launch_bounds__(kRowWarps * 32) bin_grad_kernel(Problem p, TiledWs w) {
   if (*w.flag != 0) return;
   extern __shared__ float smf[];  // [kRowWarps][kTB][Lp]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -309,26 +344,42 @@ __global__ void __launch_bounds__(kRowWarps * 32) bin_grad_kernel(Problem p, Til
   float* gs = smf + (size_t)warp * kTB * Lp;
   const int64_t rstride = p.B * p.C;
   const uint32_t* cm = w.cmask + (size_t)b * C * LW;
-  for (int64_t tb0 = t0 + (int64_t)warp * kTB; tb0 < tlive; tb0 += kRowWarps * kTB) {
+  // requests run one batch ahead: the next batch's logits and gamma rows are in flight while the current one is
+  // walked and stored
+  float xn[NCI][kTB], gn[kTB];
+  auto request = [&](int64_t tb0) {
     const int nrow = (int)min((int64_t)kTB, tlive - tb0);
-    const float* gam = w.emis + (tb0 * p.B + b) * Lmax;
-    for (int s = lane; s < Lb; s += 32) {
+    const float* gam = w.emis + (tb0 * p.B + b) * Lmax + lane;
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) gs[r * Lp + s] = r < nrow ? __ldg(gam + (int64_t)r * p.B * Lmax + s) : 0.f;
-    }
+    for (int r = 0; r < kTB; ++r) gn[r] = (r < nrow && lane < Lb) ? __ldg(gam + (int64_t)r * p.B * Lmax) : 0.f;
     const float* x0 = p.logits + (tb0 * p.B + b) * p.C;
-    float acc[NCI][kTB];
 #pragma unroll
     for (int i = 0; i < NCI; ++i) {
       const int c = lane + 32 * i;
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) acc[i][r] = (c < C && r < nrow) ? __ldg(x0 + r * rstride + c) : 0.f;
+      for (int r = 0; r < kTB; ++r) xn[i][r] = (c < C && r < nrow) ? __ldg(x0 + r * rstride + c) : 0.f;
     }
+  };
+  const int64_t tfirst = t0 + (int64_t)warp * kTB;
+  if (tfirst < tlive) request(tfirst);
+  for (int64_t tb0 = tfirst; tb0 < tlive; tb0 += kRowWarps * kTB) {
+    const int nrow = (int)min((int64_t)kTB, tlive - tb0);
+#pragma unroll
+    for (int r = 0; r < kTB; ++r) gs[r * Lp + lane] = gn[r];
+    if (Lb > 32) {  // states beyond the first 32 are not prefetched
+      const float* gam = w.emis + (tb0 * p.B + b) * Lmax;
+      for (int s = lane + 32; s < Lb; s += 32) {
+#pragma unroll
+        for (int r = 0; r < kTB; ++r) gs[r * Lp + s] = r < nrow ? __ldg(gam + (int64_t)r * p.B * Lmax + s) : 0.f;
+      }
+    }
+    float acc[NCI][kTB];
 #pragma unroll
     for (int i = 0; i < NCI; ++i) {
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) acc[i][r] = __fdividef(1.f, 1.f + __expf(-acc[i][r]));
+      for (int r = 0; r < kTB; ++r) acc[i][r] = __fdividef(1.f, 1.f + __expf(-xn[i][r]));
     }
+    if (tb0 + kRowWarps * kTB < tlive) request(tb0 + kRowWarps * kTB);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NCI; ++i) {
@@ -370,13 +421,30 @@ int launch_lattice(const Problem& p, const TiledWs& w, cudaStream_t stream) {
   return NBCTC_OK;
 }
 
+template <int NCI, int Lp>
+int launch_grad_inst(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * kRowWarps * kTB * Lp;
+  auto kern = bin_grad_kernel<NCI, Lp>;
+  if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kRowWarps * 32, smem, stream>>>(p, w);
+  NBCTC_LAUNCH_CHECK();
+  return NBCTC_OK;
+}
 template <int NCI>
 int launch_grad(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
-  const int Lp = (int)p.Lmax + 1;
-  const size_t smem = sizeof(float) * kRowWarps * kTB * Lp;
-  auto kern = bin_grad_kernel<NCI>;
+  switch (w.Lpad) {
+    case 32: return launch_grad_inst<NCI, 32>(p, w, grid, stream);
+    case 64: return launch_grad_inst<NCI, 64>(p, w, grid, stream);
+    case 128: return launch_grad_inst<NCI, 128>(p, w, grid, stream);
+    default: return launch_grad_inst<NCI, 256>(p, w, grid, stream);
+  }
+}
+template <int NCI>
+int launch_emis(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * kRowWarps * kTB * (32 * NCI + 8);
+  auto kern = bin_emis_kernel<NCI>;
   if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kRowWarps * 32, smem, stream>>>(p, w, Lp);
+  kern<<<grid, kRowWarps * 32, smem, stream>>>(p, w);
   NBCTC_LAUNCH_CHECK();
   return NBCTC_OK;
 }
@@ -416,14 +484,19 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   NBCTC_LAUNCH_CHECK();
 
   const dim3 grid((unsigned)p.B, (unsigned)((p.T + kTCh - 1) / kTCh));
-  const int Cp = (int)p.C;
-  const size_t smem1 = sizeof(float) * kRowWarps * kTB * Cp;
-  if (smem1 > 48 * 1024)
-    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(bin_emis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  bin_emis_kernel<<<grid, kRowWarps * 32, smem1, stream>>>(p, w, Cp);
-  NBCTC_LAUNCH_CHECK();
-
   int rc;
+  const int nci = (int)((p.C + 31) / 32);
+  switch (nci) {
+    case 1: rc = launch_emis<1>(p, w, grid, stream); break;
+    case 2: rc = launch_emis<2>(p, w, grid, stream); break;
+    case 3: rc = launch_emis<3>(p, w, grid, stream); break;
+    case 4: rc = launch_emis<4>(p, w, grid, stream); break;
+    case 5: rc = launch_emis<5>(p, w, grid, stream); break;
+    case 6: rc = launch_emis<6>(p, w, grid, stream); break;
+    case 7: rc = launch_emis<7>(p, w, grid, stream); break;
+    default: rc = launch_emis<8>(p, w, grid, stream); break;
+  }
+  if (rc != NBCTC_OK) return rc;
   switch (l.Lpad) {
     case 32: rc = launch_lattice<2>(p, w, stream); break;
     case 64: rc = launch_lattice<4>(p, w, stream); break;
@@ -432,7 +505,7 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   }
   if (rc != NBCTC_OK || p.grad == nullptr) return rc;
 
-  switch ((int)((p.C + 31) / 32)) {
+  switch (nci) {
     case 1: return launch_grad<1>(p, w, grid, stream);
     case 2: return launch_grad<2>(p, w, grid, stream);
     case 3: return launch_grad<3>(p, w, grid, stream);
