@@ -8,8 +8,8 @@
 //                      31 classes -- every kernel below then returns at once and the generic kernels (gated on the
 //                      same flag) run instead.
 //   K1 bin_emis      : CTA = one sequence x 256 time steps, warp = batches of 8 rows staged in shared memory;
-//                      row constant (1/C) sum_c softplus(x_c) and emissions e_t(s) = (1/C) sum_{c in S_s} x_t(c)
-//                      with lane = state (NoBlankBinaryCTC.py:109-112: -BCELoss(sigmoid(x_t), y_s)).
+//                      emissions p_t(s) = exp(e_t(s)), e_t(s) = (1/C) (sum_{c in S_s} x_t(c) - sum_c softplus(x_t(c)))
+//                      with lane = state (NoBlankBinaryCTC.py:109-112: e = -BCELoss(sigmoid(x_t), y_s)).
 //   K2 lattice_tile  : warp = sequence; the float64 linear-domain chain of the fused kernel (stream_kernel.cuh:
 //                      16 lanes x NS states per direction, exact power-of-two rescaling, one alpha checkpoint per
 //                      tile of 8 steps, alpha replay next to beta in phase 2) on the emission tiles;
@@ -21,6 +21,7 @@
 // HBM traffic: logits read twice, gradient written once, emission/gamma tile (T,B,Lmax) fp32 written twice and read
 // twice, checkpoints (T/8,B,Lpad) f64 -- about 1.8x the algorithmic bytes at C = 157, Lmax = 32.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "stream_kernel.cuh"
@@ -40,13 +41,12 @@ struct TiledWs {
   uint32_t* cmask;      // [B][C][LW]    states that contain the class
   double* ckpt;         // [B][NT][Lpad] alpha checkpoints
   int* cke;             // [B][NT]       their exponents
-  float* rowc;          // (T,B)         (1/C) sum_c softplus(x_c)
-  float* emis;          // (T,B,Lmax)    emissions, overwritten by gamma
+  float* emis;          // (T,B,Lmax)    emissions p_t(s), overwritten by gamma
   int LW, NT, Lpad;
 };
 
 struct Layout {
-  size_t o_lists, o_cmask, o_ckpt, o_cke, o_rowc, o_emis, total;
+  size_t o_lists, o_cmask, o_ckpt, o_cke, o_emis, total;
   int LW, NT, Lpad;
 };
 
@@ -61,7 +61,6 @@ Layout layout(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   l.o_cmask = take(sizeof(uint32_t) * (size_t)B * C * l.LW);
   l.o_ckpt = take(sizeof(double) * (size_t)B * l.NT * l.Lpad);
   l.o_cke = take(sizeof(int) * (size_t)B * l.NT);
-  l.o_rowc = take(sizeof(float) * (size_t)T * B);
   l.o_emis = take(sizeof(float) * (size_t)T * B * Lmax);
   l.total = off;
   return l;
@@ -111,6 +110,12 @@ __global__ void __launch_bounds__(256) bin_prepass_kernel(Problem p, TiledWs w) 
   if (lane < 8) w.lists[row * 8 + lane] = rec[warp][lane];
 }
 
+// 1 / (1 + exp(-v)) with the approximate ex2 and rcp units (2 ulp): 4 instructions
+__device__ __forceinline__ float sigmoid_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + stream::ex2f(-v * stream::kLog2e)));
+  return r;
+}
 __device__ __forceinline__ float softplus_fast(float v) {
   return fmaxf(v, 0.f) + __logf(1.f + __expf(-fabsf(v)));
 }
@@ -161,10 +166,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
       }
     }
 #pragma unroll
-    for (int r = 0; r < kTB; ++r) {
-      sp[r] = warp_sum(sp[r]);
-      if (lane == r && r < nrow) w.rowc[(tb0 + r) * p.B + b] = sp[r] * invC;
-    }
+    for (int r = 0; r < kTB; ++r) sp[r] = warp_sum(sp[r]);
     __syncwarp();
     for (int s0 = 0; s0 < Lb; s0 += 32) {
       const int st = s0 + lane;
@@ -196,12 +198,15 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
           }
         }
       }
-      if (valid) {
+      // p_t(s) = exp((sum_{c in S_s} x_c - sum_c softplus(x_c)) / C) <= 1, floored like the fused kernel's emissions;
+      // zeros for the states [L_b, Lmax) of the block (the lattice kernel loads whole pairs)
+      if (st < p.Lmax) {
         float* e0 = w.emis + ((tb0 * p.B + b) * p.Lmax + st);
         const int64_t estride = p.B * p.Lmax;
+        const float k2 = invC * stream::kLog2e;
 #pragma unroll
         for (int r = 0; r < kTB; ++r)
-          if (r < nrow) e0[r * estride] = d[r] * invC;
+          if (r < nrow) e0[r * estride] = valid ? fmaxf(stream::ex2f((d[r] - sp[r]) * k2), stream::kPMin) : 0.f;
       }
     }
     __syncwarp();
@@ -209,13 +214,77 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
 }
 
 // ------------------------------------------------------------------------------------ K2: lattice on emission tiles
+// Register-fed variants of stream::chain_phase1 / chain_phase2 (same arithmetic, same order): the emissions of a full
+// tile arrive in registers straight from global memory instead of through a shared-memory p-tile.
+template <int NS, int W, int TT>
+__device__ __forceinline__ void lat_phase1_regs(double (&x)[NS], stream::ChainScal& c, int lane, double* ck, int* cke, int k,
+                                                const double (&pr)[TT][NS]) {
+  using namespace stream;
+  const int hl = lane & (W - 1);
+  double sum[NS];
+  if (k > 0) {
+    c.Ea += rescale_group<NS, W>(x);
+    if (lane < W) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) ck[(k * NS + j) * W] = x[j];
+      if (lane == 0) cke[k] = c.Ea;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry);
+    else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0);
+  }
+  c.carry = 0.0;
+}
+// pr[jj]: the lane's emissions of its jj-th step (alpha walks up the tile, beta down), in the lane's state order
+template <int NS, int W, int TT, int AS>
+__device__ __forceinline__ void lat_phase2_regs(double (&x)[NS], stream::ChainScal& c, int lane, bool isb, int Eb_all,
+                                                const double (&ckv)[NS], int EaK, int k, const double (&pr)[TT][NS],
+                                                double* __restrict__ abt, double* s2_out) {
+  using namespace stream;
+  constexpr int Lpad = W * NS;
+  const int hl = lane & (W - 1);
+  double sum[NS];
+  const int d = EaK + Eb_all - c.Ez;
+  const double s1 = pow2i(d / 2);
+  const double s2 = -(pow2i(d - d / 2) * c.zinv);
+  if (lane == 0 && !isb) *s2_out = s2;
+  if (!isb) {
+    if (k == 0) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) x[j] = 0.0;
+      c.carry = (lane == 0) ? s1 : 0.0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) x[j] = ckv[j] * s1;
+    }
+  }
+  const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
+  const int sdir = isb ? -1 : 1;
+  double* dst = abt + (isb ? TT * AS : 0) + s0;
+#pragma unroll
+  for (int jj = 0; jj < TT; ++jj) {
+    const int i = isb ? (TT - 1 - jj) : jj;
+    if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry);
+    else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
+  }
+  c.carry = 0.0;
+  const int e = rescale_group<NS, W>(x);
+  if (isb) c.Eb += e;
+}
+
+// The emission tile holds p_t(s) = exp(e_t(s) - rowc_t) (K1; zeros for states >= L_b).  NS = 2 and an even Lmax: full
+// tiles go through registers (each lane loads the float pairs of its own two states, one tile ahead); everything else
+// is staged through the warp's shared-memory p-tile.
 // NS = 2: at most 72 registers, so that 28 warps share an SM (4096 sequences are then a single wave on 148 SMs)
 template <int NS>
 __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_kernel(Problem p, TiledWs w) {
   if (*w.flag != 0) return;
   using namespace stream;
   constexpr int W = 16, TT = 8, Lpad = 16 * NS, PS = Lpad + 8, AS = Lpad + 8;
-  constexpr int NPF = TT * Lpad / 32;  // emission-tile floats per lane
   constexpr int kWarpBytes = TT * PS * 4 + 2 * TT * AS * 8 + 16;
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -233,36 +302,47 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   const int NTb = (Tb + TT - 1) / TT;
   double* ck = w.ckpt + ((size_t)b * w.NT) * Lpad + (lane & (W - 1));
   int* cke = w.cke + (size_t)b * w.NT;
+  const bool isb = lane >= 16;
 
-  // emission tile k -> registers (issued one tile ahead of its use), then -> p-tile in shared memory:
-  // p_t(s) = exp(e_t(s) - rowc_t) <= 1 (floored like the fused kernel), 0 for states >= L_b and steps >= T_b
   constexpr int NPR = Lpad / 32;  // floats per lane and tile row
   const int64_t estride = p.B * (int64_t)Lmax;
   float* const e_b = w.emis + b * Lmax + lane;
-  const float* const rc_b = w.rowc + b;
   bool sv[NPR];
 #pragma unroll
   for (int q = 0; q < NPR; ++q) sv[q] = lane + 32 * q < Lb;
-  float ev[NPF], rcv = 0.f;
-  auto fetch = [&](int k) {
+  // tile k -> shared-memory p-tile (any tile; zeros beyond T_b and L_b)
+  auto stage = [&](int k) {
     const int t0 = k * TT, nv = min(TT, Tb - t0);
-    rcv = lane < nv ? __ldg(rc_b + (int64_t)(t0 + lane) * p.B) : 0.f;
     const float* pe = e_b + (int64_t)t0 * estride;
 #pragma unroll
     for (int r = 0; r < TT; ++r) {
 #pragma unroll
-      for (int q = 0; q < NPR; ++q) ev[r * NPR + q] = (r < nv && sv[q]) ? __ldg(pe + 32 * q) : 0.f;
+      for (int q = 0; q < NPR; ++q) pt[r * PS + lane + 32 * q] = (r < nv && sv[q]) ? __ldg(pe + 32 * q) : 0.f;
       pe += estride;
     }
   };
-  auto stage = [&](int k) {
-    const int nv = min(TT, Tb - k * TT);
+  // register path (NS = 2): the lane's state pair, forward (phase 1, alpha lanes of phase 2) or reversed (beta lanes)
+  const bool regs = NS == 2 && (Lmax & 1) == 0;
+  const int NTf = regs ? Tb / TT : 0;  // tiles [0, NTf) are full and take the register path
+  float2 pv[TT];
+  auto fetch2 = [&](int k, bool phase2) {
+    const bool rev = phase2 && isb;
+    const int s = rev ? (W - 1 - (lane & (W - 1))) * 2 : (lane & (W - 1)) * 2;
+    const bool okp = s < Lmax;  // the pair is inside the row (Lmax is even); states >= L_b hold zeros
+    const float* pe = w.emis + (((int64_t)k * TT + (rev ? TT - 1 : 0)) * p.B + b) * Lmax + s;
+    const int64_t step = rev ? -estride : estride;
 #pragma unroll
     for (int r = 0; r < TT; ++r) {
-      const float rc = __shfl_sync(0xffffffffu, rcv, r);
+      pv[r] = okp ? __ldg(reinterpret_cast<const float2*>(pe)) : make_float2(0.f, 0.f);
+      pe += step;
+    }
+  };
+  auto widen = [&](double (&pr)[TT][2], bool phase2) {
+    const bool rev = phase2 && isb;
 #pragma unroll
-      for (int q = 0; q < NPR; ++q)
-        pt[r * PS + lane + 32 * q] = (r < nv && sv[q]) ? fmaxf(ex2f((ev[r * NPR + q] - rc) * kLog2e), kPMin) : 0.f;
+    for (int r = 0; r < TT; ++r) {
+      pr[r][0] = (double)(rev ? pv[r].y : pv[r].x);
+      pr[r][1] = (double)(rev ? pv[r].x : pv[r].y);
     }
   };
 
@@ -274,11 +354,18 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   chain.zinv = 0.0;
   chain.Ea = 0; chain.Eb = 0; chain.Ez = 0;
   // ---- phase 1: alpha, one checkpoint per tile
-  fetch(0);
+  if (NTf > 0) fetch2(0, false);
   for (int k = 0; k < NTb; ++k) {
+    if constexpr (NS == 2) {
+      if (k < NTf) {
+        double pr[TT][2];
+        widen(pr, false);
+        if (k + 1 < NTf) fetch2(k + 1, false);
+        lat_phase1_regs<2, W, TT>(cx, chain, lane, ck, cke, k, pr);
+        continue;
+      }
+    }
     stage(k);
-    if (k + 1 < NTb) fetch(k + 1);
-    else if (p.grad != nullptr) fetch(NTb - 1);  // phase 2 starts with the last tile again
     __syncwarp();
     chain_phase1<NS, W, TT, PS>(cx, chain, lane, Tb, ck, cke, k, pt);
     __syncwarp();
@@ -286,9 +373,8 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   chain_readout<NS, W>(cx, chain, lane, Lb, &p.loss[b], 1.f, nullptr);
   if (p.grad == nullptr) return;
   // ---- phase 2: tiles downwards; lanes 0-15 replay alpha from the checkpoint, lanes 16-31 run beta
-  const bool isb = lane >= 16;
+  if (NTf > 0) fetch2(NTf - 1, true);
   for (int k = NTb - 1; k >= 0; --k) {
-    stage(k);
     double ckv[NS];
     int EaK = 0;
     if (k > 0) {
@@ -299,10 +385,22 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
 #pragma unroll
       for (int j = 0; j < NS; ++j) ckv[j] = 0.0;
     }
-    if (k > 0) fetch(k - 1);
-    __syncwarp();
     const int Eb_all = __shfl_sync(0xffffffffu, chain.Eb, 16);
-    chain_phase2<NS, W, TT, PS, AS>(cx, chain, lane, isb, Eb_all, Tb, ckv, EaK, k, pt, abt, s2p);
+    bool done = false;
+    if constexpr (NS == 2) {
+      if (k < NTf) {
+        double pr[TT][2];
+        widen(pr, true);
+        if (k > 0) fetch2(k - 1, true);
+        lat_phase2_regs<2, W, TT, AS>(cx, chain, lane, isb, Eb_all, ckv, EaK, k, pr, abt, s2p);
+        done = true;
+      }
+    }
+    if (!done) {
+      stage(k);
+      __syncwarp();
+      chain_phase2<NS, W, TT, PS, AS>(cx, chain, lane, isb, Eb_all, Tb, ckv, EaK, k, pt, abt, s2p);
+    }
     __syncwarp();
     // gamma_t(s) = alpha_t(s) beta_t(s) / Z (s2 = -1/Z and the tile exponents) -> emission tile
     const double s2 = *s2p;
@@ -321,11 +419,84 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   }
 }
 
+// ------------------------------------------------------------------------------------ row staging by TMA
+// A warp's batch = kTB rows (t..t+kTB-1, b) of the logits: each row is C floats, only 4-byte aligned when C % 4 != 0,
+// and consecutive rows are B*C floats apart.  Lanes 0..nrow-1 each move the 16-byte aligned superset of one row
+// with one cp.async.bulk into the row's slot; lane 0 arrives on the buffer's mbarrier with the byte total.  Two
+// buffers per warp: the next batch lands while the current one is worked on, at no register cost.
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst_smem, uint64_t src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
+template <int TB>
+struct RowStage {
+  unsigned char* buf;  // [2][TB][RSB] this warp's slots
+  uint64_t* bar;       // [2] this warp's mbarriers
+  uint32_t par;        // bit s = parity of the next completion of buffer s
+  int RSB;             // slot bytes = align16(4*C + 12)
+  uint64_t lim;        // end of the logits tensor
+  int64_t rstride;     // floats between consecutive rows of a sequence
+  int C, lane;
+
+  __device__ __forceinline__ void init(unsigned char* buf_, uint64_t* bar_, const Problem& p, int lane_) {
+    buf = buf_; bar = bar_; par = 0u; lane = lane_;
+    C = (int)p.C;
+    RSB = (4 * C + 12 + 15) & ~15;
+    rstride = p.B * p.C;
+    lim = reinterpret_cast<uint64_t>(p.logits) + (uint64_t)p.T * p.B * p.C * 4u;
+    if (lane < 2) stream::mbar_init(&bar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+  }
+  // rows x0 + r*rstride, r < nrow -> buffer s (every lane of the warp calls this)
+  __device__ __forceinline__ void issue(int s, const float* x0, int nrow) {
+    uint32_t bytes = 0;
+    if (lane < nrow) {
+      const uint64_t a = reinterpret_cast<uint64_t>(x0 + lane * rstride);
+      const uint64_t a0 = a & ~uint64_t(15);
+      uint64_t a1 = (a + 4u * C + 15) & ~uint64_t(15);
+      unsigned char* dst = buf + (size_t)(s * TB + lane) * RSB;
+      if (a1 > lim) {
+        // the tensor's last row ends inside a 16-byte chunk: the bulk copy stops before it, the rest goes by hand
+        a1 = lim & ~uint64_t(15);
+        for (uint64_t q = max(a1, a); q < a + 4u * C; q += 4)
+          *reinterpret_cast<float*>(dst + (q - a0)) = __ldg(reinterpret_cast<const float*>(q));
+      }
+      if (a1 > a0) {
+        bytes = (uint32_t)(a1 - a0);
+        bulk_g2s_plain(stream::smem_u32(dst), a0, bytes, stream::smem_u32(&bar[s]));
+      }
+    }
+    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);  // also orders the by-hand stores before the arrival
+    if (lane == 0) {
+      if (total) stream::mbar_arrive_expect_tx(&bar[s], total);  // the phase cannot complete before this arrival
+      else stream::mbar_arrive(&bar[s]);
+    }
+  }
+  __device__ __forceinline__ void wait(int s) {
+    stream::mbar_wait(&bar[s], (par >> s) & 1u);
+    par ^= 1u << s;
+  }
+  // row r of buffer s, first float of the row (rows keep their 16-byte phase)
+  __device__ __forceinline__ const float* row(int s, int r, const float* x0) const {
+    const uint32_t ph = (uint32_t)(reinterpret_cast<uint64_t>(x0 + r * rstride) & 15u);
+    return reinterpret_cast<const float*>(buf + (size_t)(s * TB + r) * RSB + ph);
+  }
+};
+
 // ------------------------------------------------------------------------------------ K3: gradient
+// Batches of kGTB = 4 rows and 16 warps per CTA: the staging buffers of a warp are half as large, so that twice as
+// many warps share an SM (the kernel is issue-bound at 16 warps per SM).
+constexpr int kGTB = 4;
+constexpr int kGradWarps = 16;
 template <int NCI, int Lp>
-__global__ void __launch_bounds__(kRowWarps * 32) bin_grad_kernel(Problem p, TiledWs w) {
+__global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p, TiledWs w) {
   if (*w.flag != 0) return;
-  extern __shared__ float smf[];  // [kRowWarps][kTB][Lp]
+  constexpr int kTB = kGTB, kRowWarps = kGradWarps;  // this kernel's batch geometry
+  extern __shared__ __align__(128) unsigned char smg[];  // [kRowWarps][2][kTB][RSB] logits rows | [kRowWarps][kTB][Lp] gamma
+  __shared__ uint64_t bars[kRowWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
   const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
@@ -341,71 +512,98 @@ __global__ void __launch_bounds__(kRowWarps * 32) bin_grad_kernel(Problem p, Til
   if (!ok || t0 >= Tb) return;
   const int Lb = (int)Lb64, LW = w.LW, Lmax = (int)p.Lmax;
   const float wC = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f) / (float)C;
-  float* gs = smf + (size_t)warp * kTB * Lp;
-  const int64_t rstride = p.B * p.C;
+  RowStage<kTB> rs;
+  const int RSB = (4 * C + 12 + 15) & ~15;
+  rs.init(smg + (size_t)warp * 2 * kTB * RSB, bars[warp], p, lane);
+  // gamma tile of the warp: [kTB][Lp + 1]; column Lp stays zero (what a lane with no state left adds)
+  constexpr int LS = Lp + 1;
+  float* gs = reinterpret_cast<float*>(smg + (size_t)kRowWarps * 2 * kTB * RSB) + (size_t)warp * kTB * LS;
+  if (lane < kTB) gs[lane * LS + Lp] = 0.f;
+  const int64_t rstride = rs.rstride;
+  const int64_t gstride = p.B * (int64_t)Lmax;
   const uint32_t* cm = w.cmask + (size_t)b * C * LW;
-  // requests run one batch ahead: the next batch's logits and gamma rows are in flight while the current one is
-  // walked and stored
-  float xn[NCI][kTB], gn[kTB];
-  auto request = [&](int64_t tb0) {
-    const int nrow = (int)min((int64_t)kTB, tlive - tb0);
-    const float* gam = w.emis + (tb0 * p.B + b) * Lmax + lane;
+  const float* const gam_b = w.emis + b * Lmax + lane;
+  const bool lane_state = lane < Lb;
+  // requests run one batch ahead: the next batch's logits (TMA) and gamma rows (registers) are in flight while the
+  // current one is walked and stored
+  float gn[kTB];
+  auto request_gamma = [&](int64_t tb0, int nrow) {
+    const float* g = gam_b + tb0 * gstride;
 #pragma unroll
-    for (int r = 0; r < kTB; ++r) gn[r] = (r < nrow && lane < Lb) ? __ldg(gam + (int64_t)r * p.B * Lmax) : 0.f;
-    const float* x0 = p.logits + (tb0 * p.B + b) * p.C;
-#pragma unroll
-    for (int i = 0; i < NCI; ++i) {
-      const int c = lane + 32 * i;
-#pragma unroll
-      for (int r = 0; r < kTB; ++r) xn[i][r] = (c < C && r < nrow) ? __ldg(x0 + r * rstride + c) : 0.f;
+    for (int r = 0; r < kTB; ++r) {
+      gn[r] = (r < nrow && lane_state) ? __ldg(g) : 0.f;
+      g += gstride;
     }
   };
+  auto x_of = [&](int64_t tb0) { return p.logits + (tb0 * p.B + b) * p.C; };
+  auto rows_of = [&](int64_t tb0) { return (int)min((int64_t)kTB, tlive - tb0); };
   const int64_t tfirst = t0 + (int64_t)warp * kTB;
-  if (tfirst < tlive) request(tfirst);
-  for (int64_t tb0 = tfirst; tb0 < tlive; tb0 += kRowWarps * kTB) {
-    const int nrow = (int)min((int64_t)kTB, tlive - tb0);
+  if (tfirst < tlive) {
+    rs.issue(0, x_of(tfirst), rows_of(tfirst));
+    request_gamma(tfirst, rows_of(tfirst));
+  }
+  int sb = 0;
+  // one batch; kFull: all kTB rows are live (no per-row predicates)
+  auto batch = [&](int64_t tb0, auto full) {
+    constexpr bool kFull = decltype(full)::value;
+    const int nrow = kFull ? kTB : rows_of(tb0);
+    const int64_t tnext = tb0 + kRowWarps * kTB;
+    if (tnext < tlive) rs.issue(sb ^ 1, x_of(tnext), rows_of(tnext));
 #pragma unroll
-    for (int r = 0; r < kTB; ++r) gs[r * Lp + lane] = gn[r];
+    for (int r = 0; r < kTB; ++r) gs[r * LS + lane] = gn[r];
     if (Lb > 32) {  // states beyond the first 32 are not prefetched
       const float* gam = w.emis + (tb0 * p.B + b) * Lmax;
       for (int s = lane + 32; s < Lb; s += 32) {
 #pragma unroll
-        for (int r = 0; r < kTB; ++r) gs[r * Lp + s] = r < nrow ? __ldg(gam + (int64_t)r * p.B * Lmax + s) : 0.f;
+        for (int r = 0; r < kTB; ++r) gs[r * LS + s] = r < nrow ? __ldg(gam + r * gstride + s) : 0.f;
       }
     }
+    if (tnext < tlive) request_gamma(tnext, rows_of(tnext));
+    rs.wait(sb);
+    const float* x0 = x_of(tb0);
     float acc[NCI][kTB];
 #pragma unroll
-    for (int i = 0; i < NCI; ++i) {
+    for (int r = 0; r < kTB; ++r) {
+      const float* xr = rs.row(sb, r, x0) + lane;
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) acc[i][r] = __fdividef(1.f, 1.f + __expf(-xn[i][r]));
+      for (int i = 0; i < NCI; ++i) {
+        const float v = ((i + 1 < NCI || lane + 32 * i < C) && (kFull || r < nrow)) ? xr[32 * i] : 0.f;
+        acc[i][r] = sigmoid_fast(v);
+      }
     }
-    if (tb0 + kRowWarps * kTB < tlive) request(tb0 + kRowWarps * kTB);
     __syncwarp();
+    // sum_s gamma_t(s) over the states of the lane's classes: the warp runs as many rounds as its fullest mask
+    // needs (uniform trip count); a lane whose mask is used up reads the zero column
 #pragma unroll
     for (int i = 0; i < NCI; ++i) {
       const int c = lane + 32 * i;
       for (int wd = 0; wd < LW; ++wd) {
-        uint32_t m = c < C ? __ldg(cm + (size_t)c * LW + wd) : 0u;
+        uint32_t m = (i + 1 < NCI || c < C) ? __ldg(cm + (size_t)c * LW + wd) : 0u;
+        const int rounds = __reduce_max_sync(0xffffffffu, __popc(m));
         const float* gw = gs + wd * 32;
-        while (m) {
-          const float* col = gw + (__ffs(m) - 1);
+        for (int k = 0; k < rounds; ++k) {
+          const float* col = m ? gw + (__ffs(m) - 1) : gs + Lp;
           m &= m - 1u;
 #pragma unroll
-          for (int r = 0; r < kTB; ++r) acc[i][r] -= col[r * Lp];
+          for (int r = 0; r < kTB; ++r) acc[i][r] -= col[r * LS];
         }
       }
     }
-    float* g0 = p.grad + (tb0 * p.B + b) * p.C;
+    float* g0 = p.grad + (tb0 * p.B + b) * p.C + lane;
 #pragma unroll
-    for (int i = 0; i < NCI; ++i) {
-      const int c = lane + 32 * i;
-      if (c < C) {
+    for (int r = 0; r < kTB; ++r) {
+      if (kFull || r < nrow) {
 #pragma unroll
-        for (int r = 0; r < kTB; ++r)
-          if (r < nrow) g0[r * rstride + c] = wC * acc[i][r];
+        for (int i = 0; i < NCI; ++i)
+          if (i + 1 < NCI || lane + 32 * i < C) g0[32 * i] = wC * acc[i][r];
       }
+      g0 += rstride;
     }
-    __syncwarp();
+    __syncwarp();  // every lane is done with buffer sb and the gamma tile before they are refilled
+  };
+  for (int64_t tb0 = tfirst; tb0 < tlive; tb0 += kRowWarps * kTB, sb ^= 1) {
+    if (tb0 + kTB <= tlive) batch(tb0, std::true_type{});
+    else batch(tb0, std::false_type{});
   }
 }
 
@@ -423,10 +621,11 @@ int launch_lattice(const Problem& p, const TiledWs& w, cudaStream_t stream) {
 
 template <int NCI, int Lp>
 int launch_grad_inst(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * kRowWarps * kTB * Lp;
+  const size_t RSB = (4 * (size_t)p.C + 12 + 15) & ~(size_t)15;
+  const size_t smem = (size_t)kGradWarps * 2 * kGTB * RSB + sizeof(float) * kGradWarps * kGTB * (Lp + 1);
   auto kern = bin_grad_kernel<NCI, Lp>;
   if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kRowWarps * 32, smem, stream>>>(p, w);
+  kern<<<grid, kGradWarps * 32, smem, stream>>>(p, w);
   NBCTC_LAUNCH_CHECK();
   return NBCTC_OK;
 }
@@ -473,7 +672,6 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   w.cmask = reinterpret_cast<uint32_t*>(c + l.o_cmask);
   w.ckpt = reinterpret_cast<double*>(c + l.o_ckpt);
   w.cke = reinterpret_cast<int*>(c + l.o_cke);
-  w.rowc = reinterpret_cast<float*>(c + l.o_rowc);
   w.emis = reinterpret_cast<float*>(c + l.o_emis);
   w.LW = l.LW; w.NT = l.NT; w.Lpad = l.Lpad;
   *flag_out = w.flag;
