@@ -116,8 +116,10 @@ __device__ __forceinline__ float sigmoid_fast(float v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + stream::ex2f(-v * stream::kLog2e)));
   return r;
 }
-__device__ __forceinline__ float softplus_fast(float v) {
-  return fmaxf(v, 0.f) + __logf(1.f + __expf(-fabsf(v)));
+__device__ __forceinline__ float lg2f_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ------------------------------------------------------------------------------------ K1: emissions
@@ -142,28 +144,39 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
   float v[NCI][kTB];
   auto request = [&](int64_t tb0) {
     const int nrow = (int)min((int64_t)kTB, tend - tb0);
-    const float* x0 = p.logits + (tb0 * p.B + b) * p.C;
+    const float* xr = p.logits + (tb0 * p.B + b) * p.C + lane;
 #pragma unroll
-    for (int i = 0; i < NCI; ++i) {
-      const int c = lane + 32 * i;
+    for (int r = 0; r < kTB; ++r) {
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) v[i][r] = (c < C && r < nrow) ? __ldg(x0 + r * rstride + c) : 0.f;
+      for (int i = 0; i < NCI; ++i) v[i][r] = ((i + 1 < NCI || lane + 32 * i < C) && r < nrow) ? __ldg(xr + 32 * i) : 0.f;
+      xr += rstride;
     }
   };
   for (int64_t tb0 = t0 + (int64_t)warp * kTB; tb0 < tend; tb0 += kRowWarps * kTB) {
     const int nrow = (int)min((int64_t)kTB, tend - tb0);
     request(tb0);
+    // sum_c softplus(x_c) = sum_c max(x_c, 0) + log prod_c (1 + exp(-|x_c|)): every factor is in (1, 2], so the
+    // product of a lane's NCI <= 8 factors cannot overflow and one lg2 per lane and row replaces one per element
     float sp[kTB];
+    {
+      float pos[kTB], prod[kTB];
 #pragma unroll
-    for (int r = 0; r < kTB; ++r) sp[r] = 0.f;
+      for (int r = 0; r < kTB; ++r) { pos[r] = 0.f; prod[r] = 1.f; }
 #pragma unroll
-    for (int i = 0; i < NCI; ++i) {
-      const int c = lane + 32 * i;
+      for (int i = 0; i < NCI; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = i + 1 < NCI || c < C;
 #pragma unroll
-      for (int r = 0; r < kTB; ++r) {
-        xs[r * Cp + c] = v[i][r];
-        sp[r] += c < C ? softplus_fast(v[i][r]) : 0.f;
+        for (int r = 0; r < kTB; ++r) {
+          const float x = v[i][r];
+          xs[r * Cp + c] = x;
+          const float f = 1.f + stream::ex2f(-fabsf(x) * stream::kLog2e);
+          pos[r] += in ? fmaxf(x, 0.f) : 0.f;
+          prod[r] *= in ? f : 1.f;
+        }
       }
+#pragma unroll
+      for (int r = 0; r < kTB; ++r) sp[r] = fmaf(lg2f_fast(prod[r]), 0.6931471805599453f, pos[r]);
     }
 #pragma unroll
     for (int r = 0; r < kTB; ++r) sp[r] = warp_sum(sp[r]);
@@ -543,6 +556,15 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
     request_gamma(tfirst, rows_of(tfirst));
   }
   int sb = 0;
+  // Lmax <= 32: the lane's class masks and the warp's round counts stay in registers for the whole CTA
+  uint32_t mreg[NCI];
+  int rreg[NCI];
+#pragma unroll
+  for (int i = 0; i < NCI; ++i) {
+    const int c = lane + 32 * i;
+    mreg[i] = (LW == 1 && (i + 1 < NCI || c < C)) ? __ldg(cm + c) : 0u;
+    rreg[i] = __reduce_max_sync(0xffffffffu, __popc(mreg[i]));
+  }
   // one batch; kFull: all kTB rows are live (no per-row predicates)
   auto batch = [&](int64_t tb0, auto full) {
     constexpr bool kFull = decltype(full)::value;
@@ -578,8 +600,12 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
     for (int i = 0; i < NCI; ++i) {
       const int c = lane + 32 * i;
       for (int wd = 0; wd < LW; ++wd) {
-        uint32_t m = (i + 1 < NCI || c < C) ? __ldg(cm + (size_t)c * LW + wd) : 0u;
-        const int rounds = __reduce_max_sync(0xffffffffu, __popc(m));
+        uint32_t m = mreg[i];
+        int rounds = rreg[i];
+        if (LW != 1) {
+          m = (i + 1 < NCI || c < C) ? __ldg(cm + (size_t)c * LW + wd) : 0u;
+          rounds = __reduce_max_sync(0xffffffffu, __popc(m));
+        }
         const float* gw = gs + wd * 32;
         for (int k = 0; k < rounds; ++k) {
           const float* col = m ? gw + (__ffs(m) - 1) : gs + Lp;
