@@ -72,7 +72,8 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
   const bool use_fused = shape_ok && fused_pointers_ok(p);
   if (use_fused) {
     rc = fused_launch(p, binary, ws, ws_bytes, stream);
-  } else if (binary && !(flags & NBCTC_FLAG_GENERIC) && tiled_bin_supported(p.T, p.B, p.C, p.Lmax)) {
+  } else if (binary && !(flags & NBCTC_FLAG_GENERIC) && tiled_bin_supported(p.T, p.B, p.C, p.Lmax) &&
+             (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {  // the TMA row copies read 16-byte aligned supersets
     // multi-label: whether the tiled kernels can take the call depends on the target VALUES (exact {0,1}, at most 31
     // classes per state), which only the device sees: workspace = [generic | tiled]; the pre-pass sets a flag and
     // either the tiled kernels or the gated generic kernels do the work

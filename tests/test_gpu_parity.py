@@ -338,6 +338,70 @@ def test_unaligned_tensors_take_the_generic_path(nb, off):
     assert rel_l2(grad, ref["grad"]) < TOL
 
 
+def _device_call_bin(nb, x, y, il, tl, seq_w=None, w_scalar=1.0, offset_floats=0, grad_offset_floats=0, flags=0):
+    """nbbctc_loss_grad_f32 through ctypes with DEVICE pointers; optional 4-byte offsets of logits / gradient."""
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    T, B, C = x.shape
+    xs = torch.empty(x.size + offset_floats, device=DEV)
+    xd = xs[offset_floats:].view(T, B, C)
+    xd.copy_(torch.tensor(x))
+    gs = torch.full((x.size + grad_offset_floats,), float("nan"), device=DEV)
+    gd = gs[grad_offset_floats:].view(T, B, C)
+    yd = torch.tensor(y, device=DEV, dtype=torch.float32)
+    ild, tld = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    per = torch.full((B,), float("nan"), device=DEV)
+    swd = None if seq_w is None else torch.tensor(seq_w, device=DEV, dtype=torch.float32)
+    wsb = int(lib.nbctc_workspace_bytes(T, B, C, y.shape[1], 1, flags))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
+    rc = lib.nbbctc_loss_grad_f32(xd.data_ptr(), T, B, C, yd.data_ptr(), y.shape[1], ild.data_ptr(), tld.data_ptr(),
+                                  per.data_ptr(), None, None, None if flags & 2 else gd.data_ptr(),
+                                  None if swd is None else swd.data_ptr(), w_scalar, ws.data_ptr(), wsb, flags,
+                                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.nbctc_last_error()
+    torch.cuda.synchronize()
+    return per.cpu().double().numpy(), gd.cpu().double().numpy()
+
+
+@pytest.mark.parametrize("off", [(0, 0), (1, 0), (0, 3), (2, 1)], ids=lambda o: "x%d_g%d" % o)
+def test_bctc_tiled_path_pointer_alignment(nb, off):
+    """The tiled multi-label path stages logits rows with 16-byte aligned bulk copies: an unaligned logits pointer must
+    take the generic kernels; the gradient pointer may have any 4-byte alignment; ragged input lengths."""
+    x, y, il, tl = make_bctc_case(77, 45, 6, 157, 11, density=0.04)
+    il = np.array([45, 44, 17, 11, 30, 45], np.int64)
+    tl = np.minimum(tl, il)
+    per, grad = _device_call_bin(nb, x, y, il, tl, offset_floats=off[0], grad_offset_floats=off[1])
+    ref = oracle("bctc", x, y, il, tl, "sum")
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    assert rel_l2(grad, ref["grad"]) < TOL
+    for b in range(6):
+        assert np.all(grad[il[b]:, b] == 0.0)
+
+
+def test_bctc_tiled_path_weights_and_no_grad(nb):
+    x, y, il, tl = make_bctc_case(78, 70, 5, 64, 9, density=0.06)
+    sw = np.array([1.0, 0.0, -2.0, 0.5, 3.0], np.float32)
+    per, grad = _device_call_bin(nb, x, y, il, tl, seq_w=sw, w_scalar=0.25)
+    ref = oracle("bctc", x, y, il, tl, "sum")
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    assert rel_l2(grad, ref["grad"] * (0.25 * sw)[None, :, None]) < TOL
+    assert np.all(grad[:, sw == 0] == 0.0)
+    per2, grad2 = _device_call_bin(nb, x, y, il, tl, flags=2)  # NBCTC_FLAG_NO_GRAD: loss only, gradient untouched
+    np.testing.assert_allclose(per2, ref["per_seq"], rtol=TOL)
+    assert np.all(np.isnan(grad2))
+
+
+def test_bctc_tiled_path_last_row_ends_inside_a_chunk(nb):
+    """T*B*C*4 not a multiple of 16: the bulk copy of the tensor's last row stops early and the rest goes by hand."""
+    for (T, B, C) in ((9, 3, 7), (8, 1, 157), (17, 5, 33)):
+        x, y, il, tl = make_bctc_case(79 + C, T, B, C, 4, density=0.2)
+        il[:] = T
+        per, grad = _device_call_bin(nb, x, y, il, tl)
+        ref = oracle("bctc", x, y, il, tl, "sum")
+        np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+        assert rel_l2(grad, ref["grad"]) < TOL
+
+
 @pytest.mark.parametrize("shape", [(19, 3, 7, 5), (23, 7, 157, 12), (16, 6, 66, 9), (9, 13, 5, 4), (40, 9, 1030, 20)],
                          ids=lambda s: "T%d_B%d_C%d_L%d" % s)
 def test_slab_alignment_phases(nb, shape):
