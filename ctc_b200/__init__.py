@@ -7,10 +7,10 @@ it has not been built (``python -m ctc_b200.build``).  There is no CPU fallback.
 from ._ffi import FLAG_DEFAULT, FLAG_GENERIC, FLAG_NO_GRAD, NbctcError, launch_count  # noqa: F401
 from .function import best_path, no_blank_binary_ctc_loss, no_blank_ctc_loss  # noqa: F401
 from .modules import NoBlankBinaryCTC, NoBlankCTC  # noqa: F401
-from .dist import ShardedLoss, all_reduce_sum, shard_batch  # noqa: F401
+from .dist import ShardedLoss, all_reduce_sum, all_reduce_sum_async, shard_batch  # noqa: F401
 
 __all__ = [
     "NoBlankCTC", "NoBlankBinaryCTC", "no_blank_ctc_loss", "no_blank_binary_ctc_loss", "best_path",
-    "ShardedLoss", "all_reduce_sum", "shard_batch", "NbctcError", "launch_count",
+    "ShardedLoss", "all_reduce_sum", "all_reduce_sum_async", "shard_batch", "NbctcError", "launch_count",
     "FLAG_DEFAULT", "FLAG_GENERIC", "FLAG_NO_GRAD",
 ]

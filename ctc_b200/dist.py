@@ -26,6 +26,40 @@ class _AllReduceSum(torch.autograd.Function):
         return g, None
 
 
+class _AllReduceSumAsync(torch.autograd.Function):
+    """As _AllReduceSum, but the collective is only ENQUEUED (``async_op=True``): the caller's stream is not made to
+    wait for it, so the next step's kernels overlap the all-reduce latency.  The handle is kept on ``holder``."""
+
+    @staticmethod
+    def forward(ctx, x, group, holder):
+        y = x.detach().clone()
+        holder.append(dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+class _Done:
+    def wait(self):
+        return True
+
+
+def all_reduce_sum_async(x: torch.Tensor, group=None):
+    """Autograd-transparent all-reduce(sum) that does not block the current stream.
+
+    Returns ``(y, work)``.  ``y.backward()`` may be called at once (the gradient of a sum over ranks does not depend
+    on its value); ``work.wait()`` must be called before ``y`` is READ on the current stream (it makes that stream
+    wait for the collective, not the host).  With one rank: ``(x, <no-op handle>)``.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x, _Done()
+    holder = []
+    y = _AllReduceSumAsync.apply(x, group, holder)
+    return y, holder[0]
+
+
 def all_reduce_sum(x: torch.Tensor, group=None) -> torch.Tensor:
     """Autograd-transparent all-reduce(sum); identity when torch.distributed is not initialised."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -49,24 +83,29 @@ class ShardedLoss(torch.nn.Module):
     ``total_batch=..., out64=True`` does exactly that.
     """
 
-    def __init__(self, local_sum_fn, group=None):
+    def __init__(self, local_sum_fn, group=None, async_reduce=False):
         super().__init__()
         self.local_sum_fn = local_sum_fn
         self.group = group
+        self.async_reduce = async_reduce
 
     def forward(self, logits, targets, input_length, target_length, total_batch=None):
+        """Mean loss over the global batch.  ``async_reduce=True``: returns ``(loss_float64, work)`` -- call
+        ``loss.backward()`` right away and ``work.wait()`` before reading the value (see all_reduce_sum_async)."""
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         if total_batch is None:
             total_batch = logits.shape[1] * world      # equal shards
         local = self.local_sum_fn(logits, targets, input_length, target_length, total_batch)
+        if self.async_reduce:
+            return all_reduce_sum_async(local, self.group)
         return all_reduce_sum(local, self.group).to(torch.float32)
 
 
-def sharded_no_blank_ctc(binary: bool = False, group=None) -> ShardedLoss:
+def sharded_no_blank_ctc(binary: bool = False, group=None, async_reduce: bool = False) -> ShardedLoss:
     from .function import no_blank_binary_ctc_loss, no_blank_ctc_loss
     fn = no_blank_binary_ctc_loss if binary else no_blank_ctc_loss
 
     def local(logits, targets, il, tl, total_batch):
         return fn(logits, targets, il, tl, "mean", total_batch=total_batch, out64=True)
 
-    return ShardedLoss(local, group)
+    return ShardedLoss(local, group, async_reduce)

@@ -46,6 +46,14 @@ def _worker(rank, world, port, out):
     ref = R.nbctc_loss_grad(x, lab, il, tl, "mean")
     ok = abs(float(loss) - ref["loss"]) < 1e-5 * abs(ref["loss"])
     ok &= np.allclose(xl.grad.numpy(), ref["grad"][:, lo:hi], atol=1e-12)
+    # the same with the all-reduce only enqueued: backward first, the value after work.wait()
+    amod = ShardedLoss(lambda *a: _OracleSum.apply(*a), async_reduce=True)
+    xa = torch.tensor(np.ascontiguousarray(x[:, lo:hi]), dtype=torch.float64, requires_grad=True)
+    aloss, work = amod(xa, torch.tensor(lab[lo:hi]), torch.tensor(il[lo:hi]), torch.tensor(tl[lo:hi]), total_batch=B)
+    aloss.backward()
+    work.wait()
+    ok &= abs(float(aloss) - ref["loss"]) < 1e-5 * abs(ref["loss"])
+    ok &= np.allclose(xa.grad.numpy(), ref["grad"][:, lo:hi], atol=1e-12)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
