@@ -530,7 +530,8 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
   rs.init(smg + (size_t)warp * 2 * kTB * RSB, bars[warp], p, lane);
   // gamma tile of the warp: [kTB][Lp + 1]; column Lp stays zero (what a lane with no state left adds)
   constexpr int LS = Lp + 1;
-  float* gs = reinterpret_cast<float*>(smg + (size_t)kRowWarps * 2 * kTB * RSB) + (size_t)warp * kTB * LS;
+  float* gs_all = reinterpret_cast<float*>(smg + (size_t)kRowWarps * 2 * kTB * RSB);
+  float* gs = gs_all + (size_t)warp * kTB * LS;
   if (lane < kTB) gs[lane * LS + Lp] = 0.f;
   const int64_t rstride = rs.rstride;
   const int64_t gstride = p.B * (int64_t)Lmax;
@@ -556,14 +557,26 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
     request_gamma(tfirst, rows_of(tfirst));
   }
   int sb = 0;
-  // Lmax <= 32: the lane's class masks and the warp's round counts stay in registers for the whole CTA
-  uint32_t mreg[NCI];
+  // Lmax <= 32: the states of every class, decoded once per CTA into a shared-memory table rt[round][class] of
+  // gamma-tile columns (ascending state order; used-up rounds point at the zero column); rreg = the warp's rounds
+  constexpr int kCs = 32 * NCI;
+  unsigned char* rt = reinterpret_cast<unsigned char*>(gs_all + (size_t)kRowWarps * kTB * LS);
   int rreg[NCI];
 #pragma unroll
   for (int i = 0; i < NCI; ++i) {
     const int c = lane + 32 * i;
-    mreg[i] = (LW == 1 && (i + 1 < NCI || c < C)) ? __ldg(cm + c) : 0u;
-    rreg[i] = __reduce_max_sync(0xffffffffu, __popc(mreg[i]));
+    const uint32_t m = (LW == 1 && (i + 1 < NCI || c < C)) ? __ldg(cm + c) : 0u;
+    rreg[i] = __reduce_max_sync(0xffffffffu, __popc(m));
+  }
+  if (LW == 1) {
+    for (int c = threadIdx.x; c < kCs; c += kRowWarps * 32) {
+      uint32_t m = c < C ? __ldg(cm + c) : 0u;
+      for (int k = 0; k < 32; ++k) {
+        rt[k * kCs + c] = (unsigned char)(m ? __ffs(m) - 1 : Lp);
+        m &= m - 1u;
+      }
+    }
+    __syncthreads();  // (every warp of the CTA gets here: the exits above do not depend on the warp)
   }
   // one batch; kFull: all kTB rows are live (no per-row predicates)
   auto batch = [&](int64_t tb0, auto full) {
@@ -599,19 +612,24 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
 #pragma unroll
     for (int i = 0; i < NCI; ++i) {
       const int c = lane + 32 * i;
-      for (int wd = 0; wd < LW; ++wd) {
-        uint32_t m = mreg[i];
-        int rounds = rreg[i];
-        if (LW != 1) {
-          m = (i + 1 < NCI || c < C) ? __ldg(cm + (size_t)c * LW + wd) : 0u;
-          rounds = __reduce_max_sync(0xffffffffu, __popc(m));
-        }
-        const float* gw = gs + wd * 32;
-        for (int k = 0; k < rounds; ++k) {
-          const float* col = m ? gw + (__ffs(m) - 1) : gs + Lp;
-          m &= m - 1u;
+      if (LW == 1) {
+        const unsigned char* rc = rt + c;
+        for (int k = 0; k < rreg[i]; ++k) {
+          const float* col = gs + rc[k * kCs];
 #pragma unroll
           for (int r = 0; r < kTB; ++r) acc[i][r] -= col[r * LS];
+        }
+      } else {
+        for (int wd = 0; wd < LW; ++wd) {
+          uint32_t m = (i + 1 < NCI || c < C) ? __ldg(cm + (size_t)c * LW + wd) : 0u;
+          const int rounds = __reduce_max_sync(0xffffffffu, __popc(m));
+          const float* gw = gs + wd * 32;
+          for (int k = 0; k < rounds; ++k) {
+            const float* col = m ? gw + (__ffs(m) - 1) : gs + Lp;
+            m &= m - 1u;
+#pragma unroll
+            for (int r = 0; r < kTB; ++r) acc[i][r] -= col[r * LS];
+          }
         }
       }
     }
@@ -648,7 +666,8 @@ int launch_lattice(const Problem& p, const TiledWs& w, cudaStream_t stream) {
 template <int NCI, int Lp>
 int launch_grad_inst(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
   const size_t RSB = (4 * (size_t)p.C + 12 + 15) & ~(size_t)15;
-  const size_t smem = (size_t)kGradWarps * 2 * kGTB * RSB + sizeof(float) * kGradWarps * kGTB * (Lp + 1);
+  const size_t smem = (size_t)kGradWarps * 2 * kGTB * RSB + sizeof(float) * kGradWarps * kGTB * (Lp + 1) +
+                      (Lp == 32 ? (size_t)32 * 32 * NCI : 0);  // + the round table (Lmax <= 32)
   auto kern = bin_grad_kernel<NCI, Lp>;
   if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kGradWarps * 32, smem, stream>>>(p, w);
