@@ -391,6 +391,27 @@ def test_bctc_tiled_path_weights_and_no_grad(nb):
     assert np.all(np.isnan(grad2))
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_bctc_tiled_path_random_shapes(nb, seed):
+    """Random small shapes through the tiled multi-label path: odd and even Lmax (register-fed and staged lattice
+    tiles), T below / across the 8-step tiles and the 4-row batches, tiny and wide class dimensions, B = 1."""
+    rs = np.random.RandomState(1000 + seed)
+    T = int(rs.choice([1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 33, 64, 70, 129, 260]))
+    B = int(rs.choice([1, 2, 3, 5, 9]))
+    C = int(rs.choice([1, 2, 3, 4, 5, 31, 32, 33, 64, 100, 157, 255, 256]))
+    L = int(rs.choice([1, 2, 3, 8, 15, 16, 31, 32, 33, 40, 64, 65, 130]))
+    dens = float(rs.choice([0.0, 0.02, 0.1, 0.3]))
+    if dens * C > 20:
+        dens = 20.0 / C  # stay on the tiled path (at most 31 classes per state)
+    x, y, il, tl = make_bctc_case(3000 + seed, T, B, C, L, density=dens, ragged_T=bool(seed & 1))
+    x *= float(rs.choice([0.1, 1.0, 4.0]))
+    per, grad = _device_call_bin(nb, x, y, il, tl)
+    ref = oracle("bctc", x, y, il, tl, "sum")
+    np.testing.assert_allclose(per, ref["per_seq"], rtol=TOL)
+    assert rel_l2(grad, ref["grad"]) < TOL
+    assert np.all(np.isfinite(grad))
+
+
 def test_bctc_tiled_path_last_row_ends_inside_a_chunk(nb):
     """T*B*C*4 not a multiple of 16: the bulk copy of the tensor's last row stops early and the rest goes by hand."""
     for (T, B, C) in ((9, 3, 7), (8, 1, 157), (17, 5, 33)):
