@@ -22,7 +22,7 @@ struct GenericWs {
   float* emis;    // (T,B,Lmax) raw emission, overwritten by gamma
   double* alpha;  // (T,B,Lmax)
   int* bad;       // (B) label-out-of-range flag
-  const int* gate;  // null, or: run only if *gate != 0 (the fused binary kernel declined the call, nbctc_stream.cu)
+  const int* gate;  // null, or: run only if *gate != 0 (the tiled multi-label path declined the call, nbctc_bin.cu)
 };
 
 __host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lmax) {
@@ -50,7 +50,7 @@ __host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lm
 template <bool kBinary>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rowstats_kernel(Problem p, GenericWs w) {
-  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
+  if (w.gate != nullptr && *w.gate == 0) return;  // the tiled multi-label path took this call
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (row >= p.T * p.B) return;
@@ -108,11 +108,10 @@ rowstats_kernel(Problem p, GenericWs w) {
 }
 
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-lattice_kernel(Problem p, GenericWs w) {
-  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
-  extern __shared__ double sm[];  // [2][Lmax]
-  const int64_t b = blockIdx.x;
+// The CTA-per-sequence kernels below walk their (virtual) block indices with a grid-stride loop: launched as the gated
+// fallback of the tiled multi-label path they use a small grid, so that the usual "flag not set" case costs a few
+// hundred CTAs that return at once instead of one per sequence and time chunk.
+__device__ __forceinline__ void lattice_body(const Problem& p, const GenericWs& w, double* sm, int64_t b) {
   const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
   const int64_t B = p.B, L = p.Lmax;
   if (!seq_feasible(Tb, Lb, p.T, L) || w.bad[b]) {
@@ -180,12 +179,26 @@ lattice_kernel(Problem p, GenericWs w) {
     flip ^= 1;
   }
 }
+template <bool kGated>
+__global__ void __launch_bounds__(1024)
+lattice_kernel(Problem p, GenericWs w) {
+  extern __shared__ double sm[];  // [2][Lmax]
+  if (!kGated) {
+    lattice_body(p, w, sm, blockIdx.x);
+    return;
+  }
+  if (*w.gate == 0) return;  // the tiled multi-label path took this call
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    lattice_body(p, w, sm, b);
+    __syncthreads();
+  }
+}
 
 // ------------------------------------------------------------------------------------
 template <bool kBinary>
 __global__ void __launch_bounds__(kRowWarps * 32)
 grad_kernel(Problem p, GenericWs w) {
-  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
+  if (w.gate != nullptr && *w.gate == 0) return;  // the tiled multi-label path took this call
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (row >= p.T * p.B) return;
@@ -274,19 +287,16 @@ __device__ __forceinline__ BinSmem bin_setup(const Problem& p, int64_t b, int Lb
 }
 
 // emissions e[t,b,s] = (1/C) y_s . x_t and the row constant (1/C) sum_c softplus(x_c) (NoBlankBinaryCTC.py:109-112)
-__global__ void __launch_bounds__(kRowWarps * 32)
-rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
-  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
-  extern __shared__ float smf[];
+__device__ __forceinline__ void rowstats_bin_smem_body(const Problem& p, const GenericWs& w, int Cp, float* smf, int64_t b,
+                                                       int64_t chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = blockIdx.x;
   const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
   if (!seq_feasible(Tb, Lb64, p.T, p.Lmax)) {
-    if (blockIdx.y == 0 && threadIdx.x == 0) w.bad[b] = 1;
+    if (chunk == 0 && threadIdx.x == 0) w.bad[b] = 1;
     return;
   }
-  if (blockIdx.y == 0 && threadIdx.x == 0) w.bad[b] = 0;
-  const int64_t t0 = (int64_t)blockIdx.y * kBinTCh;
+  if (chunk == 0 && threadIdx.x == 0) w.bad[b] = 0;
+  const int64_t t0 = chunk * kBinTCh;
   if (t0 >= Tb) return;
   const int Lb = (int)Lb64, C = (int)p.C, CW = (C + 31) / 32;
   const BinSmem S = bin_setup(p, b, Lb, Cp, smf, C);
@@ -331,16 +341,28 @@ rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
   }
 }
 
-// grad[t,b,c] = w/C * (sigmoid(x) - sum_s gamma_t(s) y[b,s,c])
+template <bool kGated>
 __global__ void __launch_bounds__(kRowWarps * 32)
-grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
-  if (w.gate != nullptr && *w.gate == 0) return;  // the fused binary kernel took this call
+rowstats_bin_smem_kernel(Problem p, GenericWs w, int Cp, int64_t nchunk) {
   extern __shared__ float smf[];
+  if (!kGated) {
+    rowstats_bin_smem_body(p, w, Cp, smf, blockIdx.x, blockIdx.y);
+    return;
+  }
+  if (*w.gate == 0) return;  // the tiled multi-label path took this call
+  for (int64_t v = blockIdx.x; v < p.B * nchunk; v += gridDim.x) {
+    rowstats_bin_smem_body(p, w, Cp, smf, v % p.B, v / p.B);
+    __syncthreads();
+  }
+}
+
+// grad[t,b,c] = w/C * (sigmoid(x) - sum_s gamma_t(s) y[b,s,c])
+__device__ __forceinline__ void grad_bin_smem_body(const Problem& p, const GenericWs& w, int Cp, float* smf, int64_t b,
+                                                   int64_t chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = blockIdx.x;
   const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
   const int C = (int)p.C;
-  const int64_t t0 = (int64_t)blockIdx.y * kBinTCh;
+  const int64_t t0 = chunk * kBinTCh;
   const int64_t t1 = min(t0 + kBinTCh, p.T);
   const float lossb = p.loss[b];
   const bool ok = seq_feasible(Tb, Lb64, p.T, p.Lmax) && (lossb < INFINITY);
@@ -383,6 +405,21 @@ grad_bin_smem_kernel(Problem p, GenericWs w, int Cp) {
       g[c] = wgt * (a0 + a1);
     }
     __syncwarp();
+  }
+}
+
+template <bool kGated>
+__global__ void __launch_bounds__(kRowWarps * 32)
+grad_bin_smem_kernel(Problem p, GenericWs w, int Cp, int64_t nchunk) {
+  extern __shared__ float smf[];
+  if (!kGated) {
+    grad_bin_smem_body(p, w, Cp, smf, blockIdx.x, blockIdx.y);
+    return;
+  }
+  if (*w.gate == 0) return;  // the tiled multi-label path took this call
+  for (int64_t v = blockIdx.x; v < p.B * nchunk; v += gridDim.x) {
+    grad_bin_smem_body(p, w, Cp, smf, v % p.B, v / p.B);
+    __syncthreads();
   }
 }
 
@@ -443,11 +480,18 @@ int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cud
   const size_t bin_smem_rs = sizeof(float) * bin_smem_floats(p.Lmax, p.C, Cp, p.C);
   const size_t bin_smem_gr = sizeof(float) * bin_smem_floats(p.Lmax, p.C, Cp, p.Lmax);
   const bool bin_smem = binary && std::max(bin_smem_rs, bin_smem_gr) <= 200 * 1024;
-  const dim3 bin_grid((unsigned)p.B, (unsigned)((p.T + kBinTCh - 1) / kBinTCh));
+  // gated fallback: a small grid (the kernels loop over their virtual blocks), else one CTA per sequence and chunk
+  const int64_t nchunk = (p.T + kBinTCh - 1) / kBinTCh;
+  const int64_t cap = 148 * 4;
+  const dim3 bin_grid_full((unsigned)p.B, (unsigned)nchunk);
+  const unsigned bin_grid_gated = (unsigned)std::min<int64_t>(p.B * nchunk, cap);
   if (bin_smem) {
-    if (bin_smem_rs > 48 * 1024)
-      NBCTC_CUDA_CHECK(cudaFuncSetAttribute(rowstats_bin_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_rs));
-    rowstats_bin_smem_kernel<<<bin_grid, kRowWarps * 32, bin_smem_rs, stream>>>(p, w, Cp);
+    if (bin_smem_rs > 48 * 1024) {
+      NBCTC_CUDA_CHECK(cudaFuncSetAttribute(rowstats_bin_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_rs));
+      NBCTC_CUDA_CHECK(cudaFuncSetAttribute(rowstats_bin_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_rs));
+    }
+    if (gate) rowstats_bin_smem_kernel<true><<<bin_grid_gated, kRowWarps * 32, bin_smem_rs, stream>>>(p, w, Cp, nchunk);
+    else rowstats_bin_smem_kernel<false><<<bin_grid_full, kRowWarps * 32, bin_smem_rs, stream>>>(p, w, Cp, nchunk);
   } else if (binary) {
     rowstats_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
   } else {
@@ -457,16 +501,22 @@ int generic_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cud
 
   int nt = (int)std::min<int64_t>(1024, (p.Lmax + 31) / 32 * 32);
   size_t smem = 2 * sizeof(double) * p.Lmax;
-  if (smem > 48 * 1024)
-    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lattice_kernel<<<(unsigned)p.B, nt, smem, stream>>>(p, w);
+  if (smem > 48 * 1024) {
+    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(lattice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (gate) lattice_kernel<true><<<(unsigned)std::min<int64_t>(p.B, cap), nt, smem, stream>>>(p, w);
+  else lattice_kernel<false><<<(unsigned)p.B, nt, smem, stream>>>(p, w);
   NBCTC_LAUNCH_CHECK();
 
   if (p.grad) {
     if (bin_smem) {
-      if (bin_smem_gr > 48 * 1024)
-        NBCTC_CUDA_CHECK(cudaFuncSetAttribute(grad_bin_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_gr));
-      grad_bin_smem_kernel<<<bin_grid, kRowWarps * 32, bin_smem_gr, stream>>>(p, w, Cp);
+      if (bin_smem_gr > 48 * 1024) {
+        NBCTC_CUDA_CHECK(cudaFuncSetAttribute(grad_bin_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_gr));
+        NBCTC_CUDA_CHECK(cudaFuncSetAttribute(grad_bin_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_gr));
+      }
+      if (gate) grad_bin_smem_kernel<true><<<bin_grid_gated, kRowWarps * 32, bin_smem_gr, stream>>>(p, w, Cp, nchunk);
+      else grad_bin_smem_kernel<false><<<bin_grid_full, kRowWarps * 32, bin_smem_gr, stream>>>(p, w, Cp, nchunk);
     } else if (binary)
       grad_kernel<true><<<row_blocks, kRowWarps * 32, 0, stream>>>(p, w);
     else

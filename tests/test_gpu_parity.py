@@ -130,6 +130,16 @@ def test_bctc_soft_targets_and_minus_one_padding(nb):
         assert_parity(loss, grad, oracle("bctc", x, clean, il, tl))
 
 
+def test_bctc_soft_targets_large_batch_gated_fallback(nb):
+    """More sequences than the gated fallback's grid (the generic kernels then loop over their virtual blocks)."""
+    T, B, C, L = 12, 700, 6, 3
+    x, y, il, tl = make_bctc_case(9, T, B, C, L, density=0.3)
+    rs = np.random.RandomState(2)
+    y_soft = np.where(np.arange(L)[None, :, None] < tl[:, None, None], rs.uniform(size=y.shape), 0.0).astype(np.float32)
+    loss, grad = run_cuda(nb, "bctc", x, y_soft, il, tl)
+    assert_parity(loss, grad, oracle("bctc", x, y_soft, il, tl))
+
+
 @pytest.mark.parametrize("kind", ["ctc", "bctc"])
 @pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
 def test_reductions(nb, kind, reduction):
