@@ -1,4 +1,4 @@
-// Tiled path of the multi-label variant (NoBlankBinaryCTC.py): five launches, time-batched row kernels.
+// Tiled path of the multi-label variant (NoBlankBinaryCTC.py): four kernels, time-batched row kernels.
 //
 // The multi-hot targets y[b] (L_b x C) do not change over time, so every product with them is organised as
 // "decode an index once, use it for kTB = 8 time steps":
@@ -14,9 +14,10 @@
 //                      16 lanes x NS states per direction, exact power-of-two rescaling, one alpha checkpoint per
 //                      tile of 8 steps, alpha replay next to beta in phase 2) on the emission tiles;
 //                      gamma overwrites the emissions (NoBlankBinaryCTC.py:72-95 transition, read-out :58-68).
-//   K3 bin_grad      : CTA = one sequence x 256 time steps, warp = batches of 8 rows, lane = class:
-//                      grad = w/C * (sigmoid(x) - sum_{s in M_c} gamma_t(s)), the states of a class walked over its
-//                      bit mask once per batch (ascending state order: deterministic).
+//   K3 bin_grad      : CTA = one sequence x 256 time steps, 16 warps, warp = batches of 4 rows staged by TMA bulk
+//                      copies (double buffered), lane = class: grad = w/C * (sigmoid(x) - sum_{s in M_c} gamma_t(s)),
+//                      the states of a class decoded once per CTA into a round table (ascending state order:
+//                      deterministic).
 //
 // HBM traffic: logits read twice, gradient written once, emission/gamma tile (T,B,Lmax) fp32 written twice and read
 // twice, checkpoints (T/8,B,Lpad) f64 -- about 1.8x the algorithmic bytes at C = 157, Lmax = 32.
