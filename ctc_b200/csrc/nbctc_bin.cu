@@ -1,13 +1,13 @@
-// Tiled path of the multi-label variant (NoBlankBinaryCTC.py): four kernels, time-batched row kernels.
+// Tiled path of the multi-label variant (NoBlankBinaryCTC.py): three kernels, time-batched row kernels.
 //
 // The multi-hot targets y[b] (L_b x C) do not change over time, so every product with them is organised as
 // "decode an index once, use it for kTB = 8 time steps":
 //
-//   P  bin_prepass   : one warp per (b,s) target row -> the state's class list (<= 31 byte indices) and the
-//                      class -> states bit masks; raises a flag when a row is not exact {0,1} or holds more than
-//                      31 classes -- every kernel below then returns at once and the generic kernels (gated on the
-//                      same flag) run instead.
-//   K1 bin_emis      : CTA = one sequence x 256 time steps, warp = batches of 8 rows staged in shared memory;
+//   K1 bin_emis      : CTA = one sequence x 256 time steps.  First the class lists of the sequence's states (one warp
+//                      per target row: <= 31 byte indices) and, from the first chunk's CTA, the class -> states bit
+//                      masks; a row that is not exact {0,1} or holds more than 31 classes raises a flag -- the
+//                      kernels below then return at once and the generic kernels (gated on the same flag) redo the
+//                      call.  Then warp = batches of 8 rows staged in shared memory;
 //                      emissions p_t(s) = exp(e_t(s)), e_t(s) = (1/C) (sum_{c in S_s} x_t(c) - sum_c softplus(x_t(c)))
 //                      with lane = state (NoBlankBinaryCTC.py:109-112: e = -BCELoss(sigmoid(x_t), y_s)).
 //   K2 lattice_tile  : warp = sequence; the float64 linear-domain chain of the fused kernel (stream_kernel.cuh:
@@ -38,7 +38,6 @@ constexpr int kLatWarps = 4;  // sequences per CTA in K2
 
 struct TiledWs {
   int* flag;            // != 0: the targets are outside this path's domain -> generic kernels
-  uint32_t* lists;      // [B][Lmax][8]  byte 0 = class count (<= 31), bytes 1.. = class indices
   uint32_t* cmask;      // [B][C][LW]    states that contain the class
   double* ckpt;         // [B][NT][Lpad] alpha checkpoints
   int* cke;             // [B][NT]       their exponents
@@ -47,7 +46,7 @@ struct TiledWs {
 };
 
 struct Layout {
-  size_t o_lists, o_cmask, o_ckpt, o_cke, o_emis, total;
+  size_t o_cmask, o_ckpt, o_cke, o_emis, total;
   int LW, NT, Lpad;
 };
 
@@ -58,57 +57,12 @@ Layout layout(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   l.NT = (int)((T + 7) / 8);
   size_t off = 256;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  l.o_lists = take((size_t)B * Lmax * 32);
   l.o_cmask = take(sizeof(uint32_t) * (size_t)B * C * l.LW);
   l.o_ckpt = take(sizeof(double) * (size_t)B * l.NT * l.Lpad);
   l.o_cke = take(sizeof(int) * (size_t)B * l.NT);
   l.o_emis = take(sizeof(float) * (size_t)T * B * Lmax);
   l.total = off;
   return l;
-}
-
-// ------------------------------------------------------------------------------------ P: class lists and masks
-__global__ void __launch_bounds__(256) bin_prepass_kernel(Problem p, TiledWs w) {
-  __shared__ uint32_t rec[8][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
-  if (row >= p.B * p.Lmax) return;
-  const int64_t b = row / p.Lmax, s = row - b * p.Lmax;
-  const int64_t Tb = p.in_len[b], Lb = p.tgt_len[b];
-  const bool valid = seq_feasible(Tb, Lb, p.T, p.Lmax) && s < Lb;
-  if (lane < 8) rec[warp][lane] = 0u;
-  __syncwarp();
-  if (valid) {
-    unsigned char* bytes = reinterpret_cast<unsigned char*>(rec[warp]);
-    const float* y = p.targets + row * p.C;
-    const int C = (int)p.C;
-    int count = 0;
-    bool bad = false;
-    float yv[8];  // C <= 256: the whole row, loaded ahead of the ballots and atomics
-#pragma unroll
-    for (int i = 0; i < 8; ++i) yv[i] = lane + 32 * i < C ? __ldg(y + lane + 32 * i) : 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c0 = 32 * i;
-      if (c0 >= C) break;
-      const int c = c0 + lane;
-      const float v = yv[i];
-      const bool one = v == 1.f;
-      bad |= !(one || v == 0.f);
-      const unsigned m = __ballot_sync(0xffffffffu, one);
-      const int pos = count + __popc(m & ((1u << lane) - 1u));
-      if (one && pos < 31) bytes[1 + pos] = (unsigned char)c;
-      if (one) atomicOr(&w.cmask[((size_t)b * C + c) * w.LW + (s >> 5)], 1u << (s & 31));
-      count += __popc(m);
-    }
-    bad = __any_sync(0xffffffffu, bad) || count > 31;
-    if (lane == 0) {
-      bytes[0] = (unsigned char)min(count, 31);
-      if (bad) atomicOr(w.flag, 1);
-    }
-    __syncwarp();
-  }
-  if (lane < 8) w.lists[row * 8 + lane] = rec[warp][lane];
 }
 
 // 1 / (1 + exp(-v)) with the approximate ex2 and rcp units (2 ulp): 4 instructions
@@ -126,9 +80,8 @@ __device__ __forceinline__ float lg2f_fast(float x) {
 // ------------------------------------------------------------------------------------ K1: emissions
 template <int NCI>
 __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_kernel(Problem p, TiledWs w) {
-  if (*w.flag != 0) return;
   constexpr int Cp = 32 * NCI + 8;  // row stride: rows start 8 banks apart
-  extern __shared__ float smf[];  // [kRowWarps][kTB][Cp]
+  extern __shared__ float smf[];  // [kRowWarps][kTB][Cp] logits rows | [Lmax][8] class lists
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
   const int64_t Tb = p.in_len[b], Lb64 = p.tgt_len[b];
@@ -140,6 +93,43 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
   const float invC = 1.f / (float)C;
   float* xs = smf + (size_t)warp * kTB * Cp;
   const int64_t rstride = p.B * p.C;  // floats between consecutive time steps of a sequence
+  // Class lists of the sequence's states (one warp per target row): byte 0 = class count (<= 31), bytes 1.. = class
+  // indices.  A row that is not exact {0,1} or holds more than 31 classes raises the flag: the later kernels then
+  // return at once and the gated generic kernels redo the whole call.  The CTA of the sequence's first time chunk
+  // also publishes the class -> states bit masks for the gradient kernel.
+  uint32_t* sl = reinterpret_cast<uint32_t*>(smf + (size_t)kRowWarps * kTB * Cp);
+  {
+    const bool publish = blockIdx.y == 0;
+    for (int s = warp; s < Lb; s += kRowWarps) {
+      const float* y = p.targets + ((size_t)b * p.Lmax + s) * C;
+      float yv[NCI];
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) yv[i] = (i + 1 < NCI || lane + 32 * i < C) ? __ldg(y + lane + 32 * i) : 0.f;
+      uint32_t* rec = sl + s * 8;
+      if (lane < 8) rec[lane] = 0u;
+      __syncwarp();
+      unsigned char* bytes = reinterpret_cast<unsigned char*>(rec);
+      int count = 0;
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) {
+        const int c = lane + 32 * i;
+        const bool one = yv[i] == 1.f;
+        bad |= !(one || yv[i] == 0.f);
+        const unsigned m = __ballot_sync(0xffffffffu, one);
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        if (one && pos < 31) bytes[1 + pos] = (unsigned char)c;
+        if (one && publish) atomicOr(&w.cmask[((size_t)b * C + c) * w.LW + (s >> 5)], 1u << (s & 31));
+        count += __popc(m);
+      }
+      bad = __any_sync(0xffffffffu, bad) || count > 31;
+      if (lane == 0) {
+        bytes[0] = (unsigned char)min(count, 31);
+        if (bad) atomicOr(w.flag, 1);
+      }
+    }
+    __syncthreads();
+  }
   // the whole batch of a warp is in flight before its first use: one memory round trip per batch.  (Requesting the
   // next batch ahead of the walk keeps v live across it: 124 registers, two CTAs per SM, 0.34 instead of 0.26 ms.)
   float v[NCI][kTB];
@@ -187,8 +177,8 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
       const bool valid = st < Lb;
       uint32_t lw[8];
       {
-        const uint4* src = reinterpret_cast<const uint4*>(w.lists + ((size_t)b * p.Lmax + min(st, Lb - 1)) * 8);
-        const uint4 a = __ldg(src), c4 = __ldg(src + 1);
+        const uint4* src = reinterpret_cast<const uint4*>(sl + (size_t)min(st, Lb - 1) * 8);
+        const uint4 a = src[0], c4 = src[1];
         lw[0] = a.x; lw[1] = a.y; lw[2] = a.z; lw[3] = a.w;
         lw[4] = c4.x; lw[5] = c4.y; lw[6] = c4.z; lw[7] = c4.w;
       }
@@ -686,7 +676,7 @@ int launch_grad(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stre
 }
 template <int NCI>
 int launch_emis(const Problem& p, const TiledWs& w, dim3 grid, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * kRowWarps * kTB * (32 * NCI + 8);
+  const size_t smem = sizeof(float) * kRowWarps * kTB * (32 * NCI + 8) + (size_t)p.Lmax * 32;
   auto kern = bin_emis_kernel<NCI>;
   if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kRowWarps * 32, smem, stream>>>(p, w);
@@ -714,19 +704,14 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   char* c = static_cast<char*>(ws);
   TiledWs w;
   w.flag = reinterpret_cast<int*>(c);
-  w.lists = reinterpret_cast<uint32_t*>(c + l.o_lists);
   w.cmask = reinterpret_cast<uint32_t*>(c + l.o_cmask);
   w.ckpt = reinterpret_cast<double*>(c + l.o_ckpt);
   w.cke = reinterpret_cast<int*>(c + l.o_cke);
   w.emis = reinterpret_cast<float*>(c + l.o_emis);
   w.LW = l.LW; w.NT = l.NT; w.Lpad = l.Lpad;
   *flag_out = w.flag;
-  NBCTC_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, 256, stream));
-  NBCTC_CUDA_CHECK(cudaMemsetAsync(w.cmask, 0, sizeof(uint32_t) * (size_t)p.B * p.C * l.LW, stream));
-  const int64_t rows = p.B * p.Lmax;
-  bin_prepass_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p, w);
-  NBCTC_LAUNCH_CHECK();
-
+  // the flag and the class masks (set with atomicOr by the emission kernel) are contiguous: one memset
+  NBCTC_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, l.o_cmask + sizeof(uint32_t) * (size_t)p.B * p.C * l.LW, stream));
   const dim3 grid((unsigned)p.B, (unsigned)((p.T + kTCh - 1) / kTCh));
   int rc;
   const int nci = (int)((p.C + 31) / 32);
