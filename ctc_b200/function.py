@@ -8,6 +8,8 @@ skipped on the device when the upstream gradient is exactly 1 (``loss.backward()
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from . import _ffi
@@ -20,11 +22,24 @@ def _ptr(t):
 
 
 def _prep_lengths(t, device, B, name):
+    if torch.is_tensor(t) and t.dtype == torch.int64 and t.device == device and t.dim() == 1 and t.shape[0] == B \
+            and t.is_contiguous():
+        return t  # the usual case (train.py:397,399): no tensor ops at all
     if not torch.is_tensor(t):
         t = torch.as_tensor(t)
     if t.numel() != B:
         raise ValueError(f"{name} must have {B} elements, got {tuple(t.shape)}")
     return t.reshape(B).to(device=device, dtype=torch.int64).contiguous()
+
+
+_WS_BYTES = {}  # (T, B, C, Lmax, binary, flags) -> workspace bytes (a pure function of the shape: one FFI call per shape)
+
+
+def _on_device(dev):
+    """Context that makes ``dev`` current; free when it already is (small batches are host-bound)."""
+    if torch.cuda.current_device() == dev.index:
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
 
 
 def _launch(x, targets, in_len, tgt_len, binary, want_grad, w_scalar, seq_w, flags):
@@ -41,10 +56,13 @@ def _launch(x, targets, in_len, tgt_len, binary, want_grad, w_scalar, seq_w, fla
         flags |= _ffi.FLAG_NO_GRAD
     if x.data_ptr() % 16 == 0 and (grad is None or grad.data_ptr() % 16 == 0):
         flags |= _ffi.FLAG_ALIGNED16    # no workspace for the unaligned-tensor fallback (torch allocations are aligned)
-    ws_bytes = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 1 if binary else 0, flags))
+    key = (T, B, C, Lmax, binary, flags)
+    ws_bytes = _WS_BYTES.get(key)
+    if ws_bytes is None:
+        ws_bytes = _WS_BYTES[key] = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 1 if binary else 0, flags))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     fn = lib.nbbctc_loss_grad_f32 if binary else lib.nbctc_loss_grad_f32
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = fn(x.data_ptr(), T, B, C, targets.data_ptr(), Lmax, in_len.data_ptr(), tgt_len.data_ptr(),
                 per_seq.data_ptr(), loss_sum.data_ptr(), reduced.data_ptr(), _ptr(grad), _ptr(seq_w),
@@ -70,15 +88,19 @@ class _NoBlankCTCFunction(torch.autograd.Function):
         x = logits.detach()
         if x.dtype != torch.float32:
             x = x.float()
-        x = x.contiguous()
+        if not x.is_contiguous():
+            x = x.contiguous()
         if binary:
             if targets.dim() != 3 or targets.shape[0] != B or targets.shape[2] != C:
                 raise ValueError(f"multi-hot targets must be (B,Lmax,C)=({B},L,{C}), got {tuple(targets.shape)}")
-            tg = targets.detach().to(device=dev, dtype=torch.float32).contiguous()
+            tg = targets if (targets.dtype == torch.float32 and targets.device == dev and targets.is_contiguous()
+                             and not targets.requires_grad) \
+                else targets.detach().to(device=dev, dtype=torch.float32).contiguous()
         else:
             if targets.dim() != 2 or targets.shape[0] != B:
                 raise ValueError(f"labels must be (B,Lmax)=({B},L), got {tuple(targets.shape)}")
-            tg = targets.detach().to(device=dev, dtype=torch.int32).contiguous()
+            tg = targets if (targets.dtype == torch.int32 and targets.device == dev and targets.is_contiguous()) \
+                else targets.detach().to(device=dev, dtype=torch.int32).contiguous()
         il = _prep_lengths(input_length, dev, B, "input_length")
         tl = _prep_lengths(target_length, dev, B, "target_length")
         # grad mode is always off inside forward(); the caller samples it (validate() runs under no_grad)
@@ -107,7 +129,7 @@ class _NoBlankCTCFunction(torch.autograd.Function):
         T, B, C = ctx.shape
         go = grad_out.detach().to(device=grad.device, dtype=torch.float32).contiguous()
         lib = _ffi.lib()
-        with torch.cuda.device(grad.device):
+        with _on_device(grad.device):
             stream = torch.cuda.current_stream(grad.device).cuda_stream
             rc = lib.nbctc_scale_grad_f32(grad.data_ptr(), T, B, C, go.data_ptr(), 1 if ctx.per_seq_out else 0, stream)
         _ffi.check(rc, "nbctc_scale_grad_f32")
