@@ -15,6 +15,7 @@ FLAG_DEFAULT = 0
 FLAG_GENERIC = 1
 FLAG_NO_GRAD = 2
 FLAG_ALIGNED16 = 4
+FLAG_LOCKSTEP = 8
 
 _lib = None
 

@@ -70,7 +70,11 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
     return NBCTC_ERR_INVALID_ARG;
   }
   const bool use_fused = shape_ok && fused_pointers_ok(p);
-  if (use_fused) {
+  const bool use_pipe = !binary && !(flags & (NBCTC_FLAG_GENERIC | NBCTC_FLAG_LOCKSTEP)) && fused_pointers_ok(p) &&
+                        pipe_supported(p.T, p.B, p.C, p.Lmax);
+  if (use_pipe) {
+    rc = pipe_launch(p, ws, ws_bytes, stream);
+  } else if (use_fused) {
     rc = fused_launch(p, binary, ws, ws_bytes, stream);
   } else if (binary && !(flags & NBCTC_FLAG_GENERIC) && tiled_bin_supported(p.T, p.B, p.C, p.Lmax) &&
              (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {  // the TMA row copies read 16-byte aligned supersets
@@ -178,10 +182,10 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   size_t g = generic_workspace_bytes(T, B, C, Lmax);
   if (flags & NBCTC_FLAG_GENERIC) return g;
   // the generic size is kept as a floor: a call with 16-byte misaligned tensors falls back to that path
-  if (fused_supported(T, B, C, Lmax, binary != 0)) {
-    const size_t f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
-    return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
-  }
+  size_t f = 0;
+  if (fused_supported(T, B, C, Lmax, binary != 0)) f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
+  if (!binary && !(flags & NBCTC_FLAG_LOCKSTEP) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
+  if (f) return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
   if (binary && tiled_bin_supported(T, B, C, Lmax)) return align_up(g, 256) + tiled_bin_workspace_bytes(T, B, C, Lmax);
   return g;
 }

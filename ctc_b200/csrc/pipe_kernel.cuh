@@ -1,0 +1,943 @@
+// Pipeline no-blank CTC forward+backward kernel for sm_100a (single-label variant; overview in nbctc_pipe.cu).
+//
+// ONE persistent kernel, two warp roles, no CTA-wide barrier after start-up.  Work is handed out by two global
+// ticket counters; dependencies are per sequence GROUP (GB batch-adjacent sequences whose rows at one time step
+// are contiguous in the (T,B,C) tensor: a "slab") and travel through release/acquire counters in the workspace.
+//
+//   stage A  row warps    task = (group, block of TB time steps): slab by TMA bulk copy -> row log-partition
+//                         (NoBlankCTC.py:136) -> per-state emissions p_t(s) = softmax(x_t)[label_s]
+//                         (NoBlankCTC.py:96-102) and the row statistics -> aux tile (global, lives in L2)
+//   stage B  chain warps  task = sequence: alpha from t = 0 upwards in lanes 0-15 and beta from t = T_b-1
+//                         downwards in lanes 16-31 of ONE warp, the same instructions (NoBlankCTC.py:71-87; the
+//                         reference's own beta pass is commented out at :113-125, autograd does it).  They MEET IN
+//                         THE MIDDLE: the first half of the steps stores its states, the second half multiplies
+//                         the fresh state of one direction with the stored state of the other:
+//                         gamma_t(s) = alpha_t(s) beta_t(s) / Z -- every lattice column is computed once per
+//                         direction, Z = sum_s alpha beta at the meeting point.  float64, linear domain, exact
+//                         power-of-two rescaling once per 8 steps with an exponent PER LANE (neighbouring lanes
+//                         exchange their scale), so states that differ by thousands of binary orders of
+//                         magnitude across the lattice keep full precision.  -w*gamma overwrites p in the aux tile.
+//   stage C  row warps    task = (group, block of TB time steps): the slab again (L2 hit while the group's window
+//                         is resident, HBM otherwise) + the aux row by TMA, w*softmax(x) recomputed from the row
+//                         statistics in place, -w*gamma scattered into it (repeated labels accumulate in
+//                         duplicate-rank rounds: deterministic), slab -> gradient by TMA store.
+//
+// Row ticket n = stage-A task n followed by stage-C task n - lag: the window between the two stages is `lag`
+// tasks deep, which bounds the L2 footprint.  Tickets are taken in order, every dependency of a ticket belongs
+// to an earlier ticket, and waiting never blocks the consumption of slabs that already landed: no deadlock, whatever
+// the number of resident CTAs.
+//
+// Template parameters: NS (chain states per lane, Lmax <= 16*NS), LPR (lanes per row; GB = 32/LPR sequences per
+// group), CPL (16-byte chunks per lane and row).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "stream_kernel.cuh"  // PTX helpers (mbarrier, bulk copies, policies)
+
+namespace nbctc {
+
+constexpr int kPipeChainWarps = 4;
+// Warp roles are whole warpgroups with their own register budget (setmaxnreg).  The CTA's register pool is what the
+// launch allocated (threads x registers of the launch bound), so rows*32*row_regs + 4*32*chain_regs must fit in it:
+//   NS <= 4:  640 threads x 96:  16 row warps x 80 + 4 chain warps x 152
+//   NS >= 8:  512 threads x 128: 12 row warps x 88 + 4 chain warps x 232
+template <int NS>
+struct PipeTraits {
+  static constexpr int kRowWarps = NS <= 4 ? 16 : 12;
+  static constexpr int kRowRegs = NS <= 4 ? 80 : 88;
+  static constexpr int kChainRegs = NS <= 4 ? 152 : 232;
+  static constexpr int kThreads = 32 * (kRowWarps + kPipeChainWarps);
+};
+inline int pipe_row_warps(int ns) { return ns <= 4 ? 16 : 12; }
+
+struct PipeCfg {
+  int NS, Lpad, LPR, CPL, GB;
+  int RSg;      // bytes of a slab in a ring slot: round16(GB*C*4) + 32
+  int AUXF;     // floats per aux row (one group, one time step): GB*Lpad emissions / gammas + GB float2 row statistics
+  int SLOTB;    // ring slot bytes: RSg + AUXF*4
+  int D;        // ring slots per row warp
+  int NRW;      // row warps per CTA
+  int TB;       // time steps per row task
+  int TPG;      // row tasks per group = ceil(T / TB)
+  int NG;       // groups = ceil(B / GB)
+  int NGS;      // aux/ab/ex slots (groups in flight)
+  int lag;      // stage C runs `lag` tickets behind stage A
+  int nblk;     // exponent blocks per direction: ceil(ceil(T/2) / 8)
+  int phase_mask;  // bit 0 stage A, bit 1 stage B, bit 2 stage C (all set in the fused launch)
+  int want_grad;
+  int grid;
+  uint32_t o_bar, o_meta, o_ring, smem_bytes;
+  // workspace
+  int* ctr;      // [0] row ticket, [1] chain ticket
+  int4* hdr;     // [B] {T_b, L_b, largest duplicate rank, gradient weight bits}; T_b = 0 outside the parity domain
+  int2* grp;     // [NG] {longest T_b of the group, sequences in the group}
+  int* lab;      // [B][Lpad] class | duplicate rank << 22
+  int* doneA;    // [NG] finished stage-A tasks
+  int* doneB;    // [NG] finished chains
+  int* doneC;    // [NG] finished stage-C tasks
+  float* aux;    // [NGS][T][AUXF]
+  double* ab;    // [NGS][GB][T][Lpad]
+  int* ex;       // [NGS][GB][2][nblk][16]
+};
+
+int launch_pipe_ns2(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
+int launch_pipe_ns4(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
+int launch_pipe_ns8(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
+int launch_pipe_ns16(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
+int launch_pipe_prep(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
+
+#ifdef __CUDACC__
+namespace pipe {
+
+using namespace stream;
+
+constexpr int kSent = -(1 << 28);  // "no exponent": an all-zero lane
+constexpr int kRB = 8;             // chain steps between two rescales
+
+// exact 2^e; 0 below the normal range, 2^1023 above
+__device__ __forceinline__ double pow2z(int e) {
+  if (e < -1022) return 0.0;
+  return __hiloint2double((1023 + min(e, 1023)) << 20, 0);
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders generic-proxy accesses (st.global / ld.global of other threads, made visible by an acquire) with
+// async-proxy accesses (TMA reads of the same global memory) of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// a dependency that never arrives is a protocol bug: trap after ~4 s instead of hanging the GPU
+static __device__ __noinline__ void wait_timeout(const char* what, int a, int b) {
+  printf("nbctc pipe: %s timed out (block %d warp %d: %d %d)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5), a, b);
+  __trap();
+}
+
+// ============================================================================ stage B: chain warp
+template <int NS>
+struct CG {
+  static constexpr int Lpad = 16 * NS;
+  static constexpr int U = 32 / NS;             // emission prefetch depth (steps) = unroll
+  static constexpr int UO = U >= 2 ? U / 2 : 1;  // prefetch depth of the other direction's stored states
+  // Largest scale step between neighbouring lanes.  Mass crosses at most ceil(8/NS) lanes between two rescales and
+  // gains 2^DEC of scaled magnitude per crossing at worst: ceil(8/NS)*DEC stays below the float64 range.
+  static constexpr int DEC = NS == 2 ? 208 : NS == 4 ? 420 : 850;
+};
+
+template <int NS>
+__device__ __forceinline__ void ldcg_vec(const float* p, float (&v)[NS]) {
+  if constexpr (NS == 2) {
+    const float2 a = __ldcg(reinterpret_cast<const float2*>(p));
+    v[0] = a.x; v[1] = a.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NS; i += 4) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(p + i));
+      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
+    }
+  }
+}
+template <int NS>
+__device__ __forceinline__ void stcg_vec(float* p, const float (&v)[NS]) {
+  if constexpr (NS == 2) {
+    __stcg(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NS; i += 4) __stcg(reinterpret_cast<float4*>(p + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+  }
+}
+template <int NS>
+__device__ __forceinline__ void ldcg_vec(const double* p, double (&v)[NS]) {
+#pragma unroll
+  for (int i = 0; i < NS; i += 2) {
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p + i));
+    v[i] = a.x; v[i + 1] = a.y;
+  }
+}
+template <int NS>
+__device__ __forceinline__ void stcg_vec(double* p, const double (&v)[NS]) {
+#pragma unroll
+  for (int i = 0; i < NS; i += 2) __stcg(reinterpret_cast<double2*>(p + i), make_double2(v[i], v[i + 1]));
+}
+
+// x(s) <- (x(s) + x(s-1)) p(s) in the lane's position order, as fma(x(s-1), p(s), x(s) p(s)): the dependent path
+// of a step is one 64-bit shuffle and one DFMA.  `fac` = 2^(e_neighbour - e_lane) brings the neighbour lane's
+// last state into this lane's scale (0 for the first lane of a direction, whose shuffle returns its own value).
+// kSum: sum(s) = x(s) + x(s-1) before the step (beta_t(s) resp. alpha_t(s)/p_t(s)), off the dependent path.
+template <int NS, bool kSum>
+__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], double fac) {
+  double t[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) t[j] = x[j] * p[j];
+  const double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
+  const double p0f = p[0] * fac;
+  if (kSum) {
+#pragma unroll
+    for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
+    sum[0] = fma(up, fac, x[0]);
+  }
+#pragma unroll
+  for (int j = NS - 1; j >= 1; --j) x[j] = fma(x[j - 1], p[j], t[j]);
+  x[0] = fma(up, p0f, t[0]);
+}
+
+// exponent field - 1023 of the largest of NS non-negative values; kSent if that is zero / denormal / not finite
+template <int NS>
+__device__ __forceinline__ int top_exponent(const double (&v)[NS]) {
+  int hi = __double2hiint(v[0]);
+#pragma unroll
+  for (int j = 1; j < NS; ++j) hi = max(hi, __double2hiint(v[j]));
+  const int ef = hi >> 20;
+  return (ef > 0 && ef < 0x7ff) ? ef - 1023 : kSent;
+}
+
+// Rescale at the start of a block of 8 steps.  Lane scale e_l = max_{k<=l}(A_k - DEC (l-k)), A_k = absolute
+// exponent of lane k's largest state: every lane is scaled to its own magnitude unless mass from a much larger
+// lane upstream is about to arrive (mass only moves to higher positions).  Values that fall 2^-1022 below the lane
+// scale flush to zero; they are below float64 resolution of what that mass turns them into.
+template <int NS>
+__device__ __forceinline__ void block_entry(double (&x)[NS], int& e, double& fac, int hl) {
+  const int te = top_exponent<NS>(x);
+  int env = te == kSent ? kSent : e + te;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int sh = __shfl_up_sync(0xffffffffu, env, o, 16);
+    if (hl >= o && sh > kSent / 2) env = max(env, sh - CG<NS>::DEC * o);
+  }
+  const int en = env > kSent / 2 ? env : e;
+  const double sc = pow2z(e - en);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) x[j] *= sc;
+  e = en;
+  const int eu = __shfl_up_sync(0xffffffffu, en, 1, 16);
+  fac = hl == 0 ? 0.0 : pow2z(eu - en);
+}
+
+struct ChainArgs {
+  float* paux;      // emissions / gammas of this sequence at t = 0: + t*pstride + state
+  int64_t pstride;  // floats between time steps
+  double* ab;       // [T][Lpad] stored states, in the storing lane's position order
+  int* ex;          // [2][nblk][16] lane scales of the first half, per block of 8 steps
+  int nblk;
+  int Tb, Lb;
+  float wgt;
+  int want_grad;
+  float* loss_out;
+};
+
+template <int NS>
+__device__ __forceinline__ void chain_sequence(const ChainArgs& a, const int lane) {
+  using G = CG<NS>;
+  constexpr int Lpad = G::Lpad, U = G::U, UO = G::UO;
+  const int hl = lane & 15;
+  const bool isb = lane >= 16;
+  const int Tb = a.Tb, Lb = a.Lb;
+  if (Tb == 1) {  // one frame, one state: gamma = 1
+    if (lane == 0) {
+      const float p0 = __ldcg(a.paux);
+      *a.loss_out = -logf(p0);
+      if (a.want_grad) __stcg(a.paux, -a.wgt);
+    }
+    return;
+  }
+  const int Ha = (Tb + 1) >> 1, odd = Tb & 1;
+  // position q = hl*NS + j of a direction is state q for alpha and state Lpad-1-q for beta: both shift the same way
+  const int soff = isb ? Lpad - NS - hl * NS : hl * NS;  // the lane's states in memory order start here
+  const bool live = soff < Lb;
+  unsigned vmask = 0, smask = 0;  // bit j: state exists; state is the direction's start state
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int sj = isb ? Lpad - 1 - (hl * NS + j) : hl * NS + j;
+    if (sj < Lb) vmask |= 1u << j;
+    if (sj == (isb ? Lb - 1 : 0)) smask |= 1u << j;
+  }
+  double x[NS], sum[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) x[j] = ((smask >> j) & 1u) ? 1.0 : 0.0;
+  int e = 0;
+  double fac = hl == 0 ? 0.0 : 1.0;
+  const float* prow = a.paux + soff;
+  const int dirx = isb ? 1 : 0;
+
+  // raw emissions (memory order) -> the lane's position order, padded states and (first step) non-start states zeroed
+  auto to_p = [&](const float (&raw)[NS], double (&p)[NS], bool start_only) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float v = isb ? raw[NS - 1 - j] : raw[j];
+      const bool keep = ((vmask >> j) & 1u) && (!start_only || ((smask >> j) & 1u));
+      p[j] = keep ? (double)v : 0.0;
+    }
+  };
+  auto load_raw = [&](int t, bool ok, float (&raw)[NS]) {
+    if (ok && live) {
+      ldcg_vec<NS>(prow + (int64_t)t * a.pstride, raw);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) raw[j] = 0.f;
+    }
+  };
+
+  // ------------------------------------------------------------------ first half: iteration k, alpha at t = k,
+  // beta at t = T_b-1-k+odd (idle at k = 0 when T_b is odd)
+  auto t1 = [&](int k) { return isb ? Tb - 1 - k + odd : k; };
+  auto ok1 = [&](int k) { return k < Ha && (!isb || k >= odd); };
+  float pq[U][NS];
+#pragma unroll
+  for (int j = 0; j < U; ++j) load_raw(t1(j), ok1(j), pq[j]);
+  int* exw = a.ex + dirx * a.nblk * 16 + hl;
+  for (int base = 0; base < Ha; base += U) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int k = base + j;
+      if (k < Ha) {
+        if ((k & (kRB - 1)) == 0) {
+          block_entry<NS>(x, e, fac, hl);
+          if (live) __stcg(exw + (k >> 3) * 16, e);
+        }
+        double p[NS];
+        const bool special = j < 2 && base == 0;  // the first valid step of a direction is k = 0 (alpha) or k = odd (beta)
+        to_p(pq[j], p, special && k == (isb ? odd : 0));
+        load_raw(t1(k + U), ok1(k + U), pq[j]);
+        const bool valid = !(special && k == 0 && isb && odd);
+        if (special && k == 0) {
+          double xs[NS];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) xs[q] = x[q];
+          chain_step<NS, false>(x, sum, p, fac);
+#pragma unroll
+          for (int q = 0; q < NS; ++q) x[q] = valid ? x[q] : xs[q];
+        } else {
+          chain_step<NS, false>(x, sum, p, fac);
+        }
+        if (live && valid) stcg_vec<NS>(a.ab + (int64_t)t1(k) * Lpad + hl * NS, x);
+      }
+    }
+  }
+  __syncwarp();  // the other half-warp's stores are visible to this lane's loads below
+
+  // ------------------------------------------------------------------ second half: iteration k, beta at
+  // t = Ha-1-k, alpha at t = Ha+k-odd (idle at k = 0 when T_b is odd).  kp = the iteration at which the other
+  // direction stored its state of time t.
+  auto t2 = [&](int k) { return isb ? Ha - 1 - k : Ha + k - odd; };
+  auto ok2 = [&](int k) { return k < Ha && (isb || k >= odd); };
+  const double* orow = a.ab + (15 - hl) * NS;
+  const int* exr = a.ex + (1 - dirx) * a.nblk * 16 + (15 - hl);
+  double oq[UO][NS];
+  auto load_o = [&](int t, bool ok, double (&o)[NS]) {
+    if (ok && live) {
+      ldcg_vec<NS>(orow + (int64_t)t * Lpad, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) o[j] = 0.0;
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < U; ++j) load_raw(t2(j), ok2(j), pq[j]);
+#pragma unroll
+  for (int j = 0; j < UO; ++j) load_o(t2(j), ok2(j), oq[j]);
+  const int kp0 = isb ? Ha - 1 : Ha - 1 + odd;
+  const int nb1 = (Ha + kRB - 1) >> 3;  // blocks the first half stored
+  int eo = live ? __ldcg(exr + min(kp0 >> 3, nb1 - 1) * 16) : 0;
+  int eo_nxt = (live && (kp0 >> 3) >= 1) ? __ldcg(exr + ((kp0 >> 3) - 1) * 16) : 0;
+
+  block_entry<NS>(x, e, fac, hl);
+  // ---- Z = sum_s alpha_t(s) beta_t(s) at t = Ha-1 (beta lanes): beta_t(s) = sum of the beta direction's next step
+  double zinv;
+  int Ez;
+  {
+    const double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
+#pragma unroll
+    for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
+    sum[0] = fma(up, fac, x[0]);
+    double o[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) o[j] = oq[0][NS - 1 - j];
+    const int ms = top_exponent<NS>(sum), mo = top_exponent<NS>(o);
+    double part = 0.0;
+    int ep = kSent;
+    if (ms != kSent && mo != kSent) {
+      const double s1 = pow2z(-ms), s2 = pow2z(-mo);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) part = fma(sum[j] * s1, o[j] * s2, part);
+      if (part > 0.0) ep = e + eo + ms + mo;
+    }
+    int emax = ep;
+#pragma unroll
+    for (int o2 = 8; o2 > 0; o2 >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o2, 16));
+    part = ep == kSent ? 0.0 : part * pow2z(ep - emax);
+#pragma unroll
+    for (int o2 = 8; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2, 16);
+    const double zsum = __shfl_sync(0xffffffffu, part, 16);
+    emax = __shfl_sync(0xffffffffu, emax, 16);
+    const int ezf = __double2hiint(zsum) >> 20;
+    if (emax == kSent || !(zsum > 0.0) || ezf <= 0 || ezf >= 0x7ff) {
+      if (lane == 0) *a.loss_out = INFINITY;
+      zinv = 0.0;
+      Ez = 0;
+    } else {
+      const int ezz = ezf - 1023;
+      const double zhat = zsum * pow2z(-ezz);
+      Ez = emax + ezz;
+      if (lane == 0) *a.loss_out = (float)(-(log(zhat) + (double)Ez * 0.6931471805599453));
+      zinv = -(double)a.wgt / zhat;  // negative: stage C ADDS gamma' = -w*gamma to w*softmax
+    }
+  }
+  if (!a.want_grad) return;
+
+  float* grow = a.paux + soff;
+  int kp = kp0;
+  for (int base = 0; base < Ha; base += U) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int k = base + j;
+      if (k < Ha) {
+        if ((k & (kRB - 1)) == 0 && k > 0) block_entry<NS>(x, e, fac, hl);
+        if (k > 0) {
+          --kp;
+          if ((kp & 7) == 7) {  // the other direction's block of 8 steps changes
+            eo = eo_nxt;
+            eo_nxt = (live && (kp >> 3) >= 1) ? __ldcg(exr + ((kp >> 3) - 1) * 16) : 0;
+          }
+        }
+        double p[NS], o[NS];
+        to_p(pq[j], p, false);
+        load_raw(t2(k + U), ok2(k + U), pq[j]);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) o[q] = oq[j % UO][NS - 1 - q];
+        load_o(t2(k + UO), ok2(k + UO), oq[j % UO]);
+        // gamma = sum * stored * 2^(e + eo - Ez) / zhat; the power of two is split over both factors (range)
+        const int dd = e + eo - Ez;
+        const double sA = pow2z(dd >> 1), sB = pow2z(dd - (dd >> 1)) * zinv;
+        const bool special = j == 0 && base == 0;
+        const bool valid = !(special && !isb && odd);
+        if (special) {
+          double xs[NS];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) xs[q] = x[q];
+          chain_step<NS, true>(x, sum, p, fac);
+#pragma unroll
+          for (int q = 0; q < NS; ++q) x[q] = valid ? x[q] : xs[q];
+        } else {
+          chain_step<NS, true>(x, sum, p, fac);
+        }
+        float g[NS], gm[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) g[q] = (float)((sum[q] * sA) * (o[q] * sB));
+#pragma unroll
+        for (int q = 0; q < NS; ++q) gm[q] = isb ? g[NS - 1 - q] : g[q];
+        if (live && valid) stcg_vec<NS>(grow + (int64_t)t2(k) * a.pstride, gm);
+      }
+    }
+  }
+}
+
+// ============================================================================ stages A and C: row warp
+// Geometry of one (t,b) row seen as 16-byte chunks of its slab (stream_kernel.cuh: RowGeom, mask_head, mask_tail,
+// store_part, scale4).
+template <int NS, int LPR, int CPL>
+struct PRows {
+  static constexpr int Lpad = 16 * NS, GB = 32 / LPR, NSL = Lpad / LPR;
+  static_assert(NSL >= 1 && NSL <= 16, "states per lane of the gather/scatter");
+
+  const Problem& P;
+  const PipeCfg& cfg;
+  const int lane, li, seq;
+  const int C;
+  // task state
+  int64_t b0;
+  int gcnt, Tb, Lb, max_rank, ph_fixed;
+  float wgt;
+  uint32_t gbytes;
+  int labr[NSL];
+
+  __device__ __forceinline__ PRows(const Problem& P_, const PipeCfg& cfg_, int lane_)
+      : P(P_), cfg(cfg_), lane(lane_), li(lane_ & (LPR - 1)), seq(lane_ / LPR), C((int)P_.C), b0(0), gcnt(0), Tb(0), Lb(0),
+        max_rank(0), ph_fixed(-1), wgt(0.f), gbytes(0) {}
+
+  // group geometry only (producer side: TMA addresses)
+  __device__ __forceinline__ void set_group(int g) {
+    b0 = (int64_t)g * GB;
+    gcnt = (int)min((int64_t)GB, P.B - b0);
+    gbytes = (uint32_t)gcnt * (uint32_t)C * 4u;
+    ph_fixed = (((unsigned)P.B * (unsigned)C) & 3u) == 0 ? (int)((((unsigned)b0 & 3u) * ((unsigned)C & 3u)) & 3u) : -1;
+  }
+  // + per-sequence state of the consumer (lengths, weight, labels of this lane's states)
+  __device__ __forceinline__ void begin_task(int g) {
+    set_group(g);
+    Tb = 0; Lb = 0; max_rank = 0; wgt = 0.f;
+    if (seq < gcnt) {
+      const int4 h = cfg.hdr[b0 + seq];
+      Tb = h.x; Lb = h.y; max_rank = h.z; wgt = __int_as_float(h.w);
+    }
+    const int* lab_seq = cfg.lab + (b0 + min(seq, gcnt - 1)) * Lpad;
+#pragma unroll
+    for (int j = 0; j < NSL; ++j) {
+      const int st = li + j * LPR;
+      labr[j] = st < Lb ? lab_seq[st] : -1;
+    }
+  }
+
+  __device__ __forceinline__ uint64_t elem_off(int t) const { return (((uint64_t)t * P.B + b0) * P.C) * 4u; }
+  __device__ __forceinline__ int slab_phase(int t) const {
+    if (ph_fixed >= 0) return ph_fixed;
+    return (int)(((((unsigned)t & 3u) * ((unsigned)P.B & 3u) + ((unsigned)b0 & 3u)) * ((unsigned)C & 3u)) & 3u);
+  }
+  __device__ __forceinline__ RowGeom geom(int t, unsigned char* tsl) const {
+    const int fidx = slab_phase(t) + seq * C;
+    RowGeom g;
+    g.off4 = fidx & 3;
+    g.nch = (g.off4 + C + 3) >> 2;
+    g.rem = g.off4 + C - 4 * (g.nch - 1);
+    g.srow = reinterpret_cast<float4*>(tsl) + (fidx >> 2);
+    return g;
+  }
+
+  // ---------------------------------------------------------------- TMA (lane 0 only)
+  // rows of time step t -> slab: the 16-byte aligned superset; returns nothing, arrives on `bar` with the byte count
+  // (+ extra_tx bytes of a second copy the caller issues on the same barrier)
+  __device__ __forceinline__ void issue_load(unsigned char* dst, uint64_t* bar, int t, uint64_t pol, const float* aux_src,
+                                             uint32_t aux_bytes) const {
+    const uint64_t a = reinterpret_cast<uint64_t>(P.logits) + elem_off(t);
+    const uint64_t lim = reinterpret_cast<uint64_t>(P.logits) + (uint64_t)P.T * P.B * P.C * 4u;
+    const uint64_t a0 = a & ~uint64_t(15);
+    uint64_t a1 = (a + gbytes + 15) & ~uint64_t(15);
+    if (a1 > lim) {
+      // the tensor's last rows end inside a 16-byte chunk: the bulk copy stops before it, the rest goes by hand
+      a1 = lim & ~uint64_t(15);
+      const float* src = reinterpret_cast<const float*>(a1);
+      float* d = reinterpret_cast<float*>(dst + (a1 - a0));
+      const int n = (int)((a + gbytes - a1) >> 2);
+      for (int c = 0; c < n; ++c) d[c] = __ldg(src + c);
+    }
+    uint32_t tx = 0;
+    if (a1 > a0) {
+      bulk_g2s_hint(smem_u32(dst), a0, (uint32_t)(a1 - a0), smem_u32(bar), pol);
+      tx += (uint32_t)(a1 - a0);
+    }
+    if (aux_bytes) {
+      bulk_g2s_hint(smem_u32(dst + cfg.RSg), reinterpret_cast<uint64_t>(aux_src), aux_bytes, smem_u32(bar), pol);
+      tx += aux_bytes;
+    }
+    if (tx) mbar_arrive_expect_tx(bar, tx);
+    else mbar_arrive(bar);
+  }
+  // finished slab of time step t -> gradient rows: aligned interior as one bulk store, <= 3 floats per side by hand
+  __device__ __forceinline__ void issue_store(const unsigned char* slab, int t, uint64_t pol) const {
+    const uint64_t g = reinterpret_cast<uint64_t>(P.grad) + elem_off(t);
+    const uint64_t gend = g + gbytes;
+    uint64_t g0 = (g + 15) & ~uint64_t(15), g1 = gend & ~uint64_t(15);
+    const unsigned char* src = slab + (g & 15);
+    if (g1 > g0) {
+      bulk_s2g_hint(g0, smem_u32(src + (g0 - g)), (uint32_t)(g1 - g0), pol);
+    } else {
+      g0 = gend; g1 = gend;
+    }
+    for (uint64_t q = g; q < g0; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
+    for (uint64_t q = g1; q < gend; q += 4) *reinterpret_cast<float*>(q) = *reinterpret_cast<const float*>(src + (q - g));
+    bulk_commit();
+  }
+
+  __device__ __forceinline__ float group_max(float v) const {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ float group_sum(float v) const {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // chunk slot c of a row is chunk q = li + c*LPR; slots c <= CPL-3 always hold a full inner chunk
+  static __device__ __forceinline__ constexpr bool slot_is_inner(int c) { return c + 3 <= CPL; }
+  __device__ __forceinline__ float4 load_chunk(const RowGeom& g, int q) const {
+    float4 v = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+    if (q < g.nch) {
+      v = g.srow[q];
+      if (q == 0) mask_head(v, g.off4);
+      if (q == g.nch - 1) mask_tail(v, g.rem);
+    }
+    return v;
+  }
+  __device__ __forceinline__ float4 load_slot(const RowGeom& g, int c) const {
+    const int q = li + c * LPR;
+    if (slot_is_inner(c)) {
+      float4 v = g.srow[q];
+      if (c == 0 && li == 0) mask_head(v, g.off4);
+      return v;
+    }
+    return load_chunk(g, q);
+  }
+  __device__ __forceinline__ void store_chunk(const RowGeom& g, int q, const float4& y) const {
+    if (q < g.nch) {
+      const int lo = q == 0 ? g.off4 : 0, hi = q == g.nch - 1 ? g.rem : 4;
+      if (lo == 0 && hi == 4) g.srow[q] = y;
+      else store_part(g.srow + q, y, lo, hi);
+    }
+  }
+  __device__ __forceinline__ void store_slot(const RowGeom& g, int c, const float4& y) const {
+    const int q = li + c * LPR;
+    if (slot_is_inner(c) && c > 0) g.srow[q] = y;
+    else store_chunk(g, q, y);
+  }
+
+  // ---------------------------------------------------------------- stage A: one slab
+  // row maximum and sum of exponentials (NoBlankCTC.py:136) -> row statistics (m*log2e, 1/sum) and the emissions
+  // p_t(s) = softmax(x_t)[label_s] (NoBlankCTC.py:96-102) -> aux row in global memory
+  __device__ __forceinline__ void stage_a(int t, unsigned char* tsl, float* auxrow) const {
+    const bool act = t < Tb;
+    const RowGeom g = geom(t, tsl);
+    float4 v[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) v[c] = load_slot(g, c);
+    float m_l = kNegInf;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) m_l = fmaxf(m_l, fmaxf(fmaxf(v[c].x, v[c].y), fmaxf(v[c].z, v[c].w)));
+    const float ml2 = (m_l > kNegInf) ? m_l * kLog2e : 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      s0 += ex2f(fmaf(v[c].x, kLog2e, -ml2));
+      s1 += ex2f(fmaf(v[c].y, kLog2e, -ml2));
+      s2 += ex2f(fmaf(v[c].z, kLog2e, -ml2));
+      s3 += ex2f(fmaf(v[c].w, kLog2e, -ml2));
+    }
+    const float m = group_max(m_l);
+    const float cf = (m_l > kNegInf) ? ex2f((m_l - m) * kLog2e) : 0.f;  // this lane's exponentials -> row maximum
+    const float s = group_sum(((s0 + s1) + (s2 + s3)) * cf);
+    if (act) {
+      const float mb = m * kLog2e;
+      const float rs = __fdividef(1.f, s);  // 1 <= s <= C
+      float* arow = auxrow + seq * Lpad;
+      if (li == 0) __stcg(reinterpret_cast<float2*>(auxrow + GB * Lpad + 2 * seq), make_float2(mb, rs));
+      const float* yr = reinterpret_cast<const float*>(g.srow) + g.off4;
+      float xv[NSL];
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) {
+        const int l = labr[j];
+        xv[j] = yr[l >= 0 ? (l & kLabMask) : 0];
+      }
+#pragma unroll
+      for (int j = 0; j < NSL; ++j)
+        if (labr[j] >= 0) __stcg(arow + li + j * LPR, fmaxf(ex2f(fmaf(xv[j], kLog2e, -mb)) * rs, kPMin));
+    }
+  }
+
+  // ---------------------------------------------------------------- stage C: one slab
+  // slab -> w*softmax(x) in place from the stored row statistics (zeros beyond input_length),
+  // -w*gamma (aux row, shared memory) added at the label classes in duplicate-rank rounds
+  __device__ __forceinline__ void stage_c(int t, unsigned char* tsl, const float* auxs) const {
+    const bool act = t < Tb && wgt != 0.f;
+    const RowGeom g = geom(t, tsl);
+    float mb = INFINITY, sc = 0.f;  // ex2(-inf) = 0: inactive rows become zeros
+    if (act) {
+      const float2 st = *reinterpret_cast<const float2*>(auxs + GB * Lpad + 2 * seq);
+      mb = st.x;
+      sc = wgt * st.y;
+    }
+    float4 v[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) v[c] = load_slot(g, c);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      v[c].x = ex2f(fmaf(v[c].x, kLog2e, -mb)) * sc;
+      v[c].y = ex2f(fmaf(v[c].y, kLog2e, -mb)) * sc;
+      v[c].z = ex2f(fmaf(v[c].z, kLog2e, -mb)) * sc;
+      v[c].w = ex2f(fmaf(v[c].w, kLog2e, -mb)) * sc;
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) store_slot(g, c, v[c]);
+    __syncwarp();
+    float* yr = reinterpret_cast<float*>(g.srow) + g.off4;
+    float gam[NSL];
+    if (act) {
+      const float* gr = auxs + seq * Lpad;
+#pragma unroll
+      for (int j = 0; j < NSL; ++j) gam[j] = labr[j] >= 0 ? gr[li + j * LPR] : 0.f;
+    }
+    const int nr = __reduce_max_sync(0xffffffffu, act ? max_rank : 0);
+    for (int r = 0; r <= nr; ++r) {
+      if (act) {
+        // the addresses of one round are pairwise distinct: all loads first, then all stores
+        float cur[NSL];
+#pragma unroll
+        for (int j = 0; j < NSL; ++j) {
+          const int l = labr[j];
+          cur[j] = (l >= 0 && (l >> kLabBits) == r) ? yr[l & kLabMask] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NSL; ++j) {
+          const int l = labr[j];
+          if (l >= 0 && (l >> kLabBits) == r) yr[l & kLabMask] = cur[j] + gam[j];
+        }
+      }
+      if (r < nr) __syncwarp();
+    }
+  }
+};
+
+// meta word of a ring slot
+constexpr int kMetaA = 1, kMetaC = 2, kMetaLast = 8;
+
+template <int NS, int LPR, int CPL>
+__device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& cfg, unsigned char* smem_raw, int rw, int lane) {
+  using R = PRows<NS, LPR, CPL>;
+  constexpr int GB = R::GB;
+  const int D = cfg.D;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar) + rw * D;
+  int4* meta = reinterpret_cast<int4*>(smem_raw + cfg.o_meta) + rw * D;
+  unsigned char* ring = smem_raw + cfg.o_ring + (size_t)rw * D * cfg.SLOTB;
+  R prod(P, cfg, lane), cons(P, cfg, lane);
+  const bool do_a = cfg.phase_mask & 1, do_c = (cfg.phase_mask & 4) && cfg.want_grad;
+  const int NA = cfg.NG * cfg.TPG;
+  const int NTK = do_c ? NA + cfg.lag : NA;
+  const int T = (int)P.T;
+  const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  const size_t aux_row_bytes = (size_t)cfg.AUXF * 4;
+
+  // producer cursor (warp-uniform)
+  int cur_type = 0, cur_gi = 0, cur_t = 0, cur_tend = 0;
+  int pend_c = -1;   // stage-C task of the current ticket, not started yet
+  int pend_a = -1;   // stage-A task of the current ticket, waiting for its aux slot
+  bool exhausted = false;
+  int head = 0, tail = 0, inflight = 0;
+  uint32_t par = 0;
+  int cons_gi = -1, cons_type = 0;
+
+  auto aux_row = [&](int gi, int t) { return cfg.aux + ((size_t)(gi % cfg.NGS) * T + t) * cfg.AUXF; };
+  auto signal = [&](int* ctr) {
+    __syncwarp();
+    if (lane == 0) red_release_add(ctr, 1);
+  };
+  auto poll_ge = [&](const int* ctr, int want) {
+    int ok = 0;
+    if (lane == 0) ok = ld_acquire(ctr) >= want;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+  };
+
+  // returns 1 if a load was issued, 0 if the producer has to wait (or is done)
+  auto try_produce = [&]() -> int {
+    for (;;) {
+      if (cur_type == 0) {
+        if (pend_a >= 0) {
+          const int gi = pend_a / cfg.TPG, tb = pend_a - gi * cfg.TPG;
+          // the aux slot of this group was used by group gi - NGS: its last reader must be done
+          if (gi >= cfg.NGS) {
+            const int gp = gi - cfg.NGS;
+            const bool free_ = do_c ? poll_ge(cfg.doneC + gp, cfg.TPG) : poll_ge(cfg.doneB + gp, __ldg(&cfg.grp[gp].y));
+            if (!free_) return 0;
+          }
+          pend_a = -1;
+          const int Tg = __ldg(&cfg.grp[gi].x);
+          const int t0 = tb * cfg.TB, t1 = min(min(T, t0 + cfg.TB), Tg);
+          if (t1 <= t0) {
+            signal(cfg.doneA + gi);
+            continue;
+          }
+          cur_type = kMetaA; cur_gi = gi; cur_t = t0; cur_tend = t1;
+          prod.set_group(gi);
+        } else if (pend_c >= 0) {
+          const int gi = pend_c / cfg.TPG, tb = pend_c - gi * cfg.TPG;
+          if (!poll_ge(cfg.doneB + gi, __ldg(&cfg.grp[gi].y))) return 0;  // the group's chains
+          fence_proxy_async_all();  // gamma' and row statistics were written through the generic proxy
+          pend_c = -1;
+          const int Tg = __ldg(&cfg.grp[gi].x);
+          const int t0 = tb * cfg.TB, t1 = min(T, t0 + cfg.TB), tl = min(t1, Tg);
+          prod.set_group(gi);
+          // rows beyond the group's longest input: zeros, written directly (ragged batches only)
+          for (int t = max(t0, Tg); t < t1; ++t) {
+            float* dst = P.grad + ((int64_t)t * P.B + prod.b0) * P.C;
+            const int n = prod.gcnt * (int)P.C;
+            for (int c = lane; c < n; c += 32) dst[c] = 0.f;
+          }
+          if (tl <= t0) {
+            signal(cfg.doneC + gi);
+            continue;
+          }
+          cur_type = kMetaC; cur_gi = gi; cur_t = t0; cur_tend = tl;
+        } else {
+          if (exhausted) return 0;
+          int n = 0;
+          if (lane == 0) n = atomicAdd(cfg.ctr, 1);
+          n = __shfl_sync(0xffffffffu, n, 0);
+          if (n >= NTK) {
+            exhausted = true;
+            return 0;
+          }
+          if (do_a && n < NA) pend_a = n;
+          if (do_c && n - cfg.lag >= 0 && n - cfg.lag < NA) pend_c = n - cfg.lag;
+          continue;
+        }
+      }
+      // issue the load of (cur_type, cur_gi, cur_t) into slot `head`
+      const int t = cur_t++;
+      const bool last = cur_t == cur_tend;
+      unsigned char* slot = ring + (size_t)head * cfg.SLOTB;
+      if (lane == 0) {
+        meta[head] = make_int4(cur_type | (last ? kMetaLast : 0), t, cur_gi, 0);
+        if (cur_type == kMetaA) prod.issue_load(slot, &bars[head], t, pol_keep, nullptr, 0);
+        else prod.issue_load(slot, &bars[head], t, pol_stream, aux_row(cur_gi, t), (uint32_t)aux_row_bytes);
+      }
+      __syncwarp();
+      if (last) cur_type = 0;
+      head = head + 1 == D ? 0 : head + 1;
+      ++inflight;
+      return 1;
+    }
+  };
+
+  unsigned long long t_idle = 0;
+  for (;;) {
+    while (inflight < D - 1) {
+      if (!try_produce()) break;
+    }
+    if (inflight == 0) {
+      if (exhausted && cur_type == 0 && pend_a < 0 && pend_c < 0) break;
+      const unsigned long long now = gtime();
+      if (t_idle == 0) t_idle = now;
+      else if (now - t_idle > 4000000000ull) wait_timeout("row warp dependency", pend_a, pend_c);
+      __nanosleep(128);
+      continue;
+    }
+    t_idle = 0;
+    // ---- consume slot `tail`
+    mbar_wait(&bars[tail], (par >> tail) & 1u);
+    par ^= 1u << tail;
+    const int4 mt = meta[tail];
+    unsigned char* slot = ring + (size_t)tail * cfg.SLOTB;
+    const int type = mt.x & 3, t = mt.y, gi = mt.z;
+    if (gi != cons_gi || type != cons_type) {
+      cons.begin_task(gi);
+      cons_gi = gi;
+      cons_type = type;
+    }
+    if (type == kMetaA) {
+      cons.stage_a(t, slot, aux_row(gi, t));
+      if (lane == 0) bulk_commit();  // one (empty) group per consumed slot keeps the wait below uniform
+      if (mt.x & kMetaLast) {
+        fence_proxy_async_all();
+        signal(cfg.doneA + gi);
+      }
+    } else {
+      cons.stage_c(t, slot, reinterpret_cast<const float*>(slot + cfg.RSg));
+      fence_proxy_async();  // the slab is read by the async proxy (bulk store)
+      __syncwarp();
+      if (lane == 0) cons.issue_store(slot, t, pol_stream);
+      if (mt.x & kMetaLast) signal(cfg.doneC + gi);
+    }
+    tail = tail + 1 == D ? 0 : tail + 1;
+    --inflight;
+    // the slot refilled next was consumed one iteration ago: its bulk store may only be the older of two pending
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+template <int NS, int LPR>
+__device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg& cfg, int lane) {
+  constexpr int GB = 32 / LPR, Lpad = 16 * NS;
+  const int T = (int)P.T;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(cfg.ctr + 1, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= (int)P.B) break;
+    const int b = q, gi = b / GB, sq = b - gi * GB;
+    const int4 h = __ldg(&cfg.hdr[b]);
+    if (h.x > 0) {
+      // all stage-A tasks of the group
+      unsigned long long t0 = 0;
+      for (;;) {
+        int ok = 0;
+        if (lane == 0) ok = ld_acquire(cfg.doneA + gi) >= cfg.TPG;
+        if (__shfl_sync(0xffffffffu, ok, 0)) break;
+        const unsigned long long now = gtime();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) __trap();  // (no call here: a callee shared with the row warps would
+                                                      // pin the chain warps to the row warps' register budget)
+        __nanosleep(256);
+      }
+      ChainArgs a;
+      const size_t slot = (size_t)(gi % cfg.NGS);
+      a.paux = cfg.aux + (slot * T) * cfg.AUXF + sq * Lpad;
+      a.pstride = cfg.AUXF;
+      a.ab = cfg.ab + ((slot * GB + sq) * (size_t)T) * Lpad;
+      a.ex = cfg.ex + ((slot * GB + sq) * 2) * (size_t)cfg.nblk * 16;
+      a.nblk = cfg.nblk;
+      a.Tb = h.x; a.Lb = h.y; a.wgt = __int_as_float(h.w);
+      a.want_grad = cfg.want_grad;
+      a.loss_out = P.loss + b;
+      chain_sequence<NS>(a, lane);
+    }
+    __syncwarp();
+    if (lane == 0) red_release_add(cfg.doneB + gi, 1);
+  }
+}
+
+template <int NS, int LPR, int CPL>
+__global__ void __launch_bounds__(PipeTraits<NS>::kThreads, 1) nbctc_pipe_kernel(const Problem P, const PipeCfg cfg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar);
+  for (int i = tid; i < cfg.NRW * cfg.D; i += blockDim.x) mbar_init(&bars[i], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  // register budget per role (NRW is a multiple of 4: the roles are whole warpgroups)
+  // (the block always has kRowWarps row warps; those beyond cfg.NRW have no ring and leave at once)
+  if (warp < PipeTraits<NS>::kRowWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PipeTraits<NS>::kRowRegs));
+    if ((cfg.phase_mask & 5) && warp < cfg.NRW) row_warp_main<NS, LPR, CPL>(P, cfg, smem_raw, warp, lane);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PipeTraits<NS>::kChainRegs));
+    if (cfg.phase_mask & 2) chain_warp_main<NS, LPR>(P, cfg, lane);
+  }
+}
+
+template <int NS, int LPR, int CPL>
+int launch_pipe_inst(const Problem& p, const PipeCfg& cfg, cudaStream_t stream) {
+  auto kern = nbctc_pipe_kernel<NS, LPR, CPL>;
+  NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes));
+  kern<<<cfg.grid, PipeTraits<NS>::kThreads, cfg.smem_bytes, stream>>>(p, cfg);
+  NBCTC_LAUNCH_CHECK();
+  return NBCTC_OK;
+}
+
+template <int NS>
+int launch_pipe_ns(const Problem& p, const PipeCfg& cfg, cudaStream_t stream) {
+#define NBCTC_PIPE_CASE(L, Cp) \
+  if (cfg.LPR == L && cfg.CPL == Cp) return launch_pipe_inst<NS, L, Cp>(p, cfg, stream);
+#ifdef NBCTC_PIPE_FEW  // development builds: the instances of the BASELINE shapes only
+  if constexpr (NS <= 4) { NBCTC_PIPE_CASE(8, 5) }
+  if constexpr (NS == 16) { NBCTC_PIPE_CASE(32, 8) }
+#else
+  // LPR >= NS keeps the emission gather / gamma scatter at <= 16 states per lane
+  if constexpr (NS <= 4) {
+    NBCTC_PIPE_CASE(4, 1) NBCTC_PIPE_CASE(4, 2) NBCTC_PIPE_CASE(4, 3) NBCTC_PIPE_CASE(4, 4)
+  }
+  if constexpr (NS <= 8) {
+    NBCTC_PIPE_CASE(8, 2) NBCTC_PIPE_CASE(8, 3) NBCTC_PIPE_CASE(8, 4) NBCTC_PIPE_CASE(8, 5) NBCTC_PIPE_CASE(8, 6)
+    NBCTC_PIPE_CASE(8, 7) NBCTC_PIPE_CASE(8, 8)
+  }
+  NBCTC_PIPE_CASE(16, 1) NBCTC_PIPE_CASE(16, 2) NBCTC_PIPE_CASE(16, 3) NBCTC_PIPE_CASE(16, 4)
+  NBCTC_PIPE_CASE(32, 1) NBCTC_PIPE_CASE(32, 2) NBCTC_PIPE_CASE(32, 3) NBCTC_PIPE_CASE(32, 4) NBCTC_PIPE_CASE(32, 6)
+  NBCTC_PIPE_CASE(32, 8)
+#endif
+#undef NBCTC_PIPE_CASE
+  set_error("no pipeline kernel instance for NS=%d LPR=%d CPL=%d", NS, cfg.LPR, cfg.CPL);
+  return NBCTC_ERR_UNSUPPORTED;
+}
+
+}  // namespace pipe
+#endif  // __CUDACC__
+
+}  // namespace nbctc

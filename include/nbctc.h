@@ -49,6 +49,9 @@ extern "C" {
                                      then omits the room for the unaligned-tensor fallback (the call fails with
                                      NBCTC_ERR_INVALID_ARG if the promise is broken) */
 
+#define NBCTC_FLAG_LOCKSTEP 8u    /* single-label variant: use the round-1 lock-step fused kernel instead of the
+                                     pipeline kernel (cross-check / comparison) */
+
 typedef void* nbctc_stream_t; /* cudaStream_t */
 
 /* Library version (NBCTC_VERSION of the build). */
