@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -98,69 +99,144 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
   return rc;
 }
 
+// ---- host-buffer plugin call ------------------------------------------------------------
+// The batch is cut into chunks of sequences that travel through three device slots: chunk c+1 is copied in (strided
+// 2-D copy out of the (T,B,C) host tensor) while chunk c runs and the gradient of chunk c-1 is copied back, on
+// three streams.  Device buffers and streams are kept per device between calls (nbctc_host_release frees them).
+struct HostSlot {
+  float *x = nullptr, *g = nullptr, *loss = nullptr;
+  void* tg = nullptr;
+  int64_t *il = nullptr, *tl = nullptr;
+  void* ws = nullptr;
+  size_t cap_x = 0, cap_g = 0, cap_loss = 0, cap_tg = 0, cap_len = 0, cap_ws = 0;
+  cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+};
+struct HostCtx {
+  bool init = false;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  HostSlot slot[3];
+  std::mutex mu;
+};
+constexpr int kMaxDevices = 64;
+HostCtx g_host[kMaxDevices];
+
+cudaError_t grow(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
+
+void host_release(HostCtx& h) {
+  if (!h.init) return;
+  for (HostSlot& s : h.slot) {
+    cudaFree(s.x); cudaFree(s.g); cudaFree(s.loss); cudaFree(s.tg); cudaFree(s.il); cudaFree(s.tl); cudaFree(s.ws);
+    cudaEventDestroy(s.in_done); cudaEventDestroy(s.k_done); cudaEventDestroy(s.out_done);
+    s = HostSlot{};
+  }
+  cudaStreamDestroy(h.s_in); cudaStreamDestroy(h.s_k); cudaStreamDestroy(h.s_out);
+  h.init = false;
+}
+
 template <typename TargetT>
 int host_entry(int device, bool binary, const float* logits_h, int64_t T, int64_t B, int64_t C,
                const TargetT* tg_h, int64_t Lmax, const int64_t* il_h, const int64_t* tl_h,
                float* loss_h, double* loss_sum_h, float* loss_red_h, float* grad_h, float w_scalar, uint32_t flags) {
   clear_error();
   if (check_common(logits_h, T, B, C, tg_h, Lmax, il_h, tl_h, loss_h) != NBCTC_OK) return NBCTC_ERR_INVALID_ARG;
+  if (device < 0 || device >= kMaxDevices) {
+    set_error("device index %d out of range", device);
+    return NBCTC_ERR_INVALID_ARG;
+  }
   NBCTC_CUDA_CHECK(cudaSetDevice(device));
-  cudaStream_t st;
-  NBCTC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  const size_t n = (size_t)T * B * C;
-  const size_t tg_elems = binary ? (size_t)B * Lmax * C : (size_t)B * Lmax;
-  const size_t ws_bytes = nbctc_workspace_bytes(T, B, C, Lmax, binary ? 1 : 0, flags);
-  float *d_x = nullptr, *d_g = nullptr, *d_loss = nullptr;
-  TargetT* d_tg = nullptr;
-  int64_t *d_il = nullptr, *d_tl = nullptr;
-  double* d_sum = nullptr;
-  float* d_red = nullptr;
-  void* d_ws = nullptr;
-  int rc = NBCTC_OK;
-  auto cleanup = [&]() {
-    cudaFree(d_x); cudaFree(d_g); cudaFree(d_loss); cudaFree(d_tg); cudaFree(d_il); cudaFree(d_tl);
-    cudaFree(d_sum); cudaFree(d_red); cudaFree(d_ws);
-    cudaStreamDestroy(st);
-  };
+  HostCtx& h = g_host[device];
+  std::lock_guard<std::mutex> lock(h.mu);
 #define HOST_TRY(expr)                                                                   \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
     if (_e != cudaSuccess) {                                                             \
       set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                         \
-      cleanup();                                                                         \
+      cudaDeviceSynchronize();                                                           \
       return NBCTC_ERR_CUDA;                                                             \
     }                                                                                    \
   } while (0)
-  const bool want_grad = grad_h != nullptr && !(flags & NBCTC_FLAG_NO_GRAD);
-  HOST_TRY(cudaMalloc(&d_x, n * sizeof(float)));
-  if (want_grad) HOST_TRY(cudaMalloc(&d_g, n * sizeof(float)));
-  HOST_TRY(cudaMalloc(&d_loss, B * sizeof(float)));
-  HOST_TRY(cudaMalloc(&d_tg, tg_elems * sizeof(TargetT)));
-  HOST_TRY(cudaMalloc(&d_il, B * sizeof(int64_t)));
-  HOST_TRY(cudaMalloc(&d_tl, B * sizeof(int64_t)));
-  HOST_TRY(cudaMalloc(&d_sum, sizeof(double)));
-  HOST_TRY(cudaMalloc(&d_red, sizeof(float)));
-  HOST_TRY(cudaMalloc(&d_ws, ws_bytes ? ws_bytes : 256));
-  HOST_TRY(cudaMemcpyAsync(d_x, logits_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
-  HOST_TRY(cudaMemcpyAsync(d_tg, tg_h, tg_elems * sizeof(TargetT), cudaMemcpyHostToDevice, st));
-  HOST_TRY(cudaMemcpyAsync(d_il, il_h, B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  HOST_TRY(cudaMemcpyAsync(d_tl, tl_h, B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  Problem p{};
-  p.logits = d_x;
-  if (binary) p.targets = reinterpret_cast<const float*>(d_tg); else p.labels = reinterpret_cast<const int32_t*>(d_tg);
-  p.in_len = d_il; p.tgt_len = d_tl; p.loss = d_loss; p.loss_sum = d_sum; p.loss_reduced = d_red;
-  p.grad = want_grad ? d_g : nullptr; p.seq_w = nullptr; p.w_scalar = w_scalar;
-  p.T = T; p.B = B; p.C = C; p.Lmax = Lmax;
-  rc = run(p, binary, d_ws, ws_bytes, flags, st);
-  if (rc == NBCTC_OK) {
-    HOST_TRY(cudaMemcpyAsync(loss_h, d_loss, B * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (loss_sum_h) HOST_TRY(cudaMemcpyAsync(loss_sum_h, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (loss_red_h) HOST_TRY(cudaMemcpyAsync(loss_red_h, d_red, sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (want_grad) HOST_TRY(cudaMemcpyAsync(grad_h, d_g, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    HOST_TRY(cudaStreamSynchronize(st));
+  if (!h.init) {
+    HOST_TRY(cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&h.s_k, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
+    for (HostSlot& s : h.slot) {
+      HOST_TRY(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+      HOST_TRY(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+      HOST_TRY(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+    }
+    h.init = true;
   }
+  const bool want_grad = grad_h != nullptr && !(flags & NBCTC_FLAG_NO_GRAD);
+  // chunk of sequences: ~64 MB of logits, a multiple of 4 sequences (16-byte aligned slabs for any C), >= 8 chunks
+  // for a large batch so that the copies of neighbouring chunks hide the kernel
+  const int64_t row_bytes = T * C * 4;
+  int64_t Bc = std::max<int64_t>(4, (int64_t)(64e6 / (double)row_bytes) / 4 * 4);
+  Bc = std::min(Bc, std::max<int64_t>(4, ((B + 7) / 8 + 3) / 4 * 4));
+  Bc = std::min(Bc, B);
+  const int64_t nchunk = (B + Bc - 1) / Bc;
+  const size_t tg_per_seq = (size_t)Lmax * (binary ? (size_t)C : 1) * sizeof(TargetT);
+  const size_t ws_bytes = nbctc_workspace_bytes(T, Bc, C, Lmax, binary ? 1 : 0, flags);
+  const int nslot = (int)std::min<int64_t>(3, nchunk);
+  for (int i = 0; i < nslot; ++i) {
+    HostSlot& s = h.slot[i];
+    HOST_TRY(grow((void**)&s.x, &s.cap_x, (size_t)T * Bc * C * 4));
+    if (want_grad) HOST_TRY(grow((void**)&s.g, &s.cap_g, (size_t)T * Bc * C * 4));
+    HOST_TRY(grow((void**)&s.loss, &s.cap_loss, (size_t)Bc * 4));
+    HOST_TRY(grow(&s.tg, &s.cap_tg, tg_per_seq * Bc));
+    size_t cap_len2 = s.cap_len;
+    HOST_TRY(grow((void**)&s.il, &s.cap_len, (size_t)Bc * 8));
+    HOST_TRY(grow((void**)&s.tl, &cap_len2, (size_t)Bc * 8));
+    HOST_TRY(grow(&s.ws, &s.cap_ws, ws_bytes ? ws_bytes : 256));
+  }
+  int rc = NBCTC_OK;
+  for (int64_t c = 0; c < nchunk && rc == NBCTC_OK; ++c) {
+    HostSlot& s = h.slot[c % 3];
+    const int64_t b0 = c * Bc, nb = std::min(Bc, B - b0);
+    // the slot's previous occupant (chunk c-3) must have left the device
+    HOST_TRY(cudaStreamWaitEvent(h.s_in, s.out_done, 0));
+    HOST_TRY(cudaMemcpy2DAsync(s.x, (size_t)nb * C * 4, logits_h + b0 * C, (size_t)B * C * 4, (size_t)nb * C * 4, (size_t)T,
+                               cudaMemcpyHostToDevice, h.s_in));
+    HOST_TRY(cudaMemcpyAsync(s.tg, reinterpret_cast<const char*>(tg_h) + tg_per_seq * b0, tg_per_seq * nb, cudaMemcpyHostToDevice, h.s_in));
+    HOST_TRY(cudaMemcpyAsync(s.il, il_h + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, h.s_in));
+    HOST_TRY(cudaMemcpyAsync(s.tl, tl_h + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, h.s_in));
+    HOST_TRY(cudaEventRecord(s.in_done, h.s_in));
+    HOST_TRY(cudaStreamWaitEvent(h.s_k, s.in_done, 0));
+    Problem p{};
+    p.logits = s.x;
+    if (binary) p.targets = reinterpret_cast<const float*>(s.tg); else p.labels = reinterpret_cast<const int32_t*>(s.tg);
+    p.in_len = s.il; p.tgt_len = s.tl; p.loss = s.loss; p.loss_sum = nullptr; p.loss_reduced = nullptr;
+    p.grad = want_grad ? s.g : nullptr; p.seq_w = nullptr; p.w_scalar = w_scalar;
+    p.T = T; p.B = nb; p.C = C; p.Lmax = Lmax;
+    rc = run(p, binary, s.ws, s.cap_ws, flags, h.s_k);
+    if (rc != NBCTC_OK) break;
+    HOST_TRY(cudaEventRecord(s.k_done, h.s_k));
+    HOST_TRY(cudaStreamWaitEvent(h.s_out, s.k_done, 0));
+    HOST_TRY(cudaMemcpyAsync(loss_h + b0, s.loss, (size_t)nb * 4, cudaMemcpyDeviceToHost, h.s_out));
+    if (want_grad)
+      HOST_TRY(cudaMemcpy2DAsync(grad_h + b0 * C, (size_t)B * C * 4, s.g, (size_t)nb * C * 4, (size_t)nb * C * 4, (size_t)T,
+                                 cudaMemcpyDeviceToHost, h.s_out));
+    HOST_TRY(cudaEventRecord(s.out_done, h.s_out));
+  }
+  HOST_TRY(cudaStreamSynchronize(h.s_in));
+  HOST_TRY(cudaStreamSynchronize(h.s_k));
+  HOST_TRY(cudaStreamSynchronize(h.s_out));
 #undef HOST_TRY
-  cleanup();
+  if (rc != NBCTC_OK) return rc;
+  // the reduction of NoBlankCTC.py:140 over the whole batch, float64, ascending b
+  if (loss_sum_h || loss_red_h) {
+    double acc = 0.0;
+    for (int64_t b = 0; b < B; ++b) acc += (double)loss_h[b];
+    if (loss_sum_h) *loss_sum_h = acc;
+    if (loss_red_h) *loss_red_h = (float)((double)w_scalar * acc);
+  }
   return rc;
 }
 
@@ -237,6 +313,18 @@ int nbctc_scale_grad_f32(float* grad_logits, int64_t T, int64_t B, int64_t C, co
   const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 16));
   scale_grad_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(grad_logits, n4, n, B, C, grad_out, per_seq);
   NBCTC_LAUNCH_CHECK();
+  return NBCTC_OK;
+}
+
+int nbctc_host_release(int device) {
+  clear_error();
+  if (device < 0 || device >= kMaxDevices) return NBCTC_ERR_INVALID_ARG;
+  HostCtx& h = g_host[device];
+  std::lock_guard<std::mutex> lock(h.mu);
+  if (h.init) {
+    NBCTC_CUDA_CHECK(cudaSetDevice(device));
+    host_release(h);
+  }
   return NBCTC_OK;
 }
 

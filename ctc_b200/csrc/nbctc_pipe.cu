@@ -28,7 +28,7 @@ int g_env_tb = INT32_MIN, g_env_win = INT32_MIN, g_env_split = INT32_MIN, g_env_
 struct PipePlan {
   bool ok;
   PipeCfg cfg;
-  size_t o_ctr, o_hdr, o_grp, o_lab, o_doneA, o_doneB, o_doneC, o_aux, o_ab, o_ex, ws_bytes;
+  size_t o_ctr, o_hdr, o_grp, o_lab, o_doneA, o_doneB, o_doneC, o_aux, o_ab, ws_bytes;
 };
 
 // prep kernel: one CTA per group
@@ -113,9 +113,9 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   c.GB = 32 / lpr;
   c.RSg = (int)align_up((size_t)c.GB * C * 4, 16) + 32;
   c.AUXF = (int)align_up((size_t)c.GB * c.Lpad + 2 * c.GB, 4);
-  c.SLOTB = (int)align_up((size_t)c.RSg + (size_t)c.AUXF * 4, 128);
+  c.SLOTB = (int)align_up((size_t)c.RSg + (size_t)c.AUXF * 4 + (size_t)c.GB * c.Lpad * 4 + (size_t)c.GB * 16, 128);
   // ring: as many row warps and slots as fit into shared memory
-  const size_t cap = 220 * 1024;
+  const size_t cap = 222 * 1024 - (size_t)kPipeChainWarps * pipe::pipe_chain_ring_bytes(c.NS);
   const int nrw_max = pipe_row_warps(c.NS);
   c.NRW = nrw_max;
   c.D = 4;
@@ -130,27 +130,37 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
       if (t[0] <= nrw_max && fits(t[0], t[1])) { c.NRW = t[0]; c.D = t[1]; placed = true; break; }
     if (!placed) return pl;
   }
-  c.TB = std::max(1, env_int_cached("NBCTC_PIPE_TB", 16, &g_env_tb));
+  // slabs per warp and task: 1 keeps the fewest groups in flight; long sequences take more (fewer label reloads)
+  const int ks = std::max(1, env_int_cached("NBCTC_PIPE_KS", T >= 2048 ? 4 : 1, &g_env_tb));
+  c.TB = ks * c.NRW;
   c.TPG = (int)((T + c.TB - 1) / c.TB);
   c.NG = (int)((B + c.GB - 1) / c.GB);
   if ((int64_t)c.NG * c.TPG > ((int64_t)1 << 30)) return pl;
-  c.nblk = (int)(((T + 1) / 2 + 7) / 8);
-  // window between stage A and stage C in groups: sized so that logits + aux + stored states of the window stay in L2
-  const double per_group = (double)c.GB * T * (C * 4.0 + c.Lpad * 4.0 + c.Lpad * 8.0 * 0.5);
-  int win = (int)std::max(4.0, std::min(512.0, 56e6 / per_group));
+  c.grid = (int)std::max<int64_t>(1, std::min<int64_t>(148, std::max<int64_t>((int64_t)c.NG * c.TPG, (B + kPipeChainWarps - 1) / kPipeChainWarps)));
+  // Window between stage A and stage C in groups: the chains that must be in flight to keep up with the rows at
+  // ~60 % of the HBM roofline = sequence rate x chain latency (T steps of ~cyc cycles), with a margin.
+  const double t_target_us = (2.0 * 4.0 * T * B * C) / (0.6 * 6.5e6);
+  const double cyc = c.NS == 2 ? 80 : c.NS == 4 ? 110 : c.NS == 8 ? 180 : 300;
+  const double latency_us = (double)T * cyc / 1900.0 + 4.0;
+  int win = (int)(1.5 * (double)B / t_target_us * latency_us / c.GB) + 2;
   const int want_win = env_int_cached("NBCTC_PIPE_WIN", 0, &g_env_win);
   if (want_win > 0) win = want_win;
-  win = std::min(win, c.NG);
-  c.lag = std::max(1, win) * c.TPG;
+  win = std::max(1, std::min(win, c.NG));
+  // in positions of a CTA's ticket sequence; wmax * grid >= TPG + grid keeps the schedule free of deadlocks
+  c.wmax = std::max((win * c.TPG + c.grid - 1) / c.grid + 1, c.TPG / c.grid + 2);
   const bool split = env_int_cached("NBCTC_PIPE_SPLIT", 0, &g_env_split) != 0;
-  c.NGS = split ? c.NG : std::min(c.NG, win + 8);
+  // aux slots: everything stage A can be ahead of stage C, plus the groups the tickets in flight span
+  const int span = c.grid / std::max(1, c.TPG) + 2;
+  c.NGS = split ? c.NG : std::min<int64_t>(c.NG, ((int64_t)c.wmax * c.grid + c.TPG - 1) / c.TPG + 2 * span + 4);
   c.phase_mask = 7;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
   c.o_bar = take(sizeof(uint64_t) * c.NRW * c.D);
   c.o_meta = take(sizeof(int4) * c.NRW * c.D);
+  c.o_flags = take(16);
   off = align_up(off, 128);
   c.o_ring = take((size_t)c.NRW * c.D * c.SLOTB);
+  c.o_cring = take((size_t)kPipeChainWarps * pipe::pipe_chain_ring_bytes(c.NS));
   c.smem_bytes = (uint32_t)off;
   // workspace
   size_t w = 0;
@@ -162,9 +172,8 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   pl.o_doneA = wtake(sizeof(int) * (size_t)c.NG);
   pl.o_doneB = wtake(sizeof(int) * (size_t)c.NG);
   pl.o_doneC = wtake(sizeof(int) * (size_t)c.NG);
-  pl.o_aux = wtake(sizeof(float) * (size_t)c.NGS * T * c.AUXF);
-  pl.o_ab = wtake(sizeof(double) * (size_t)c.NGS * c.GB * T * c.Lpad);
-  pl.o_ex = wtake(sizeof(int) * (size_t)c.NGS * c.GB * 2 * c.nblk * 16);
+  pl.o_aux = wtake(sizeof(float) * (size_t)c.NGS * (T + 2 * pipe::kPadRows) * c.AUXF);
+  pl.o_ab = wtake(sizeof(uint32_t) * (size_t)c.NGS * c.GB * (T + 2 * pipe::kPadRows) * 16 * (c.NS + (c.NS == 2 ? 2 : 4)));
   pl.ws_bytes = w;
   pl.ok = true;
   return pl;
@@ -208,8 +217,7 @@ int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream
   c.doneB = reinterpret_cast<int*>(w + pl.o_doneB);
   c.doneC = reinterpret_cast<int*>(w + pl.o_doneC);
   c.aux = reinterpret_cast<float*>(w + pl.o_aux);
-  c.ab = reinterpret_cast<double*>(w + pl.o_ab);
-  c.ex = reinterpret_cast<int*>(w + pl.o_ex);
+  c.ab = reinterpret_cast<uint32_t*>(w + pl.o_ab);
   c.want_grad = p.grad != nullptr;
   if (g_sm_count == 0) {
     int dev = 0, n = 0;
@@ -217,10 +225,8 @@ int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream
     NBCTC_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     g_sm_count = n;
   }
-  // persistent grid: one CTA per SM, fewer when there is not enough work for all of them
-  const int64_t row_tasks = (int64_t)c.NG * c.TPG;
-  const int64_t want = std::max<int64_t>((row_tasks + c.NRW - 1) / c.NRW, (p.B + kPipeChainWarps - 1) / kPipeChainWarps);
-  c.grid = (int)std::max<int64_t>(1, std::min<int64_t>(g_sm_count, want));
+  c.grid = std::min(c.grid, g_sm_count);  // (the plan assumed 148 SMs)
+  c.wmax = std::max(c.wmax, c.TPG / c.grid + 2);
   int rc = launch_pipe_prep(p, c, stream);
   if (rc != NBCTC_OK) return rc;
   auto launch = [&](const PipeCfg& cc) {
@@ -237,7 +243,6 @@ int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream
       if (ph == 2 && !c.want_grad) break;
       PipeCfg cc = c;
       cc.phase_mask = 1 << ph;
-      cc.lag = 0;
       if (ph > 0) {
         // the ticket counters restart for every launch
         NBCTC_CUDA_CHECK(cudaMemsetAsync(c.ctr, 0, 8, stream));

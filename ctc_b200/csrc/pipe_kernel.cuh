@@ -22,10 +22,10 @@
 //                         statistics in place, -w*gamma scattered into it (repeated labels accumulate in
 //                         duplicate-rank rounds: deterministic), slab -> gradient by TMA store.
 //
-// Row ticket n = stage-A task n followed by stage-C task n - lag: the window between the two stages is `lag`
-// tasks deep, which bounds the L2 footprint.  Tickets are taken in order, every dependency of a ticket belongs
-// to an earlier ticket, and waiting never blocks the consumption of slabs that already landed: no deadlock, whatever
-// the number of resident CTAs.
+// Row tasks = (group, block of TB time steps) are dealt to the CTAs round-robin; each row warp walks its CTA's task
+// sequence twice (stage A ahead, stage C behind, stage C first whenever its chains are done): see row_warp_main.
+// Every dependency of a task belongs to tasks at earlier positions, and waiting never blocks the consumption of
+// slabs that already landed: no deadlock once every CTA of the grid runs.
 //
 // Template parameters: NS (chain states per lane, Lmax <= 16*NS), LPR (lanes per row; GB = 32/LPR sequences per
 // group), CPL (16-byte chunks per lane and row).
@@ -55,30 +55,28 @@ struct PipeCfg {
   int NS, Lpad, LPR, CPL, GB;
   int RSg;      // bytes of a slab in a ring slot: round16(GB*C*4) + 32
   int AUXF;     // floats per aux row (one group, one time step): GB*Lpad emissions / gammas + GB float2 row statistics
-  int SLOTB;    // ring slot bytes: RSg + AUXF*4
+  int SLOTB;    // ring slot bytes: slab, aux row, label buffer (GB*Lpad labels + GB headers)
   int D;        // ring slots per row warp
   int NRW;      // row warps per CTA
-  int TB;       // time steps per row task
+  int TB;       // time steps per row task (a multiple of NRW: warp w owns steps w, w + NRW, ...)
   int TPG;      // row tasks per group = ceil(T / TB)
   int NG;       // groups = ceil(B / GB)
   int NGS;      // aux/ab/ex slots (groups in flight)
-  int lag;      // stage C runs `lag` tickets behind stage A
-  int nblk;     // exponent blocks per direction: ceil(ceil(T/2) / 8)
+  int wmax;     // stage A runs at most `wmax` positions of a CTA's ticket sequence ahead of stage C
   int phase_mask;  // bit 0 stage A, bit 1 stage B, bit 2 stage C (all set in the fused launch)
   int want_grad;
   int grid;
-  uint32_t o_bar, o_meta, o_ring, smem_bytes;
+  uint32_t o_bar, o_meta, o_flags, o_ring, o_cring, smem_bytes;
   // workspace
   int* ctr;      // [0] row ticket, [1] chain ticket
   int4* hdr;     // [B] {T_b, L_b, largest duplicate rank, gradient weight bits}; T_b = 0 outside the parity domain
   int2* grp;     // [NG] {longest T_b of the group, sequences in the group}
   int* lab;      // [B][Lpad] class | duplicate rank << 22
-  int* doneA;    // [NG] finished stage-A tasks
+  int* doneA;    // [NG] finished stage-A slabs (complete = the group's longest T_b)
   int* doneB;    // [NG] finished chains
-  int* doneC;    // [NG] finished stage-C tasks
-  float* aux;    // [NGS][T][AUXF]
-  double* ab;    // [NGS][GB][T][Lpad]
-  int* ex;       // [NGS][GB][2][nblk][16]
+  int* doneC;    // [NG] finished stage-C slabs
+  float* aux;    // [NGS][T + 2 kPadRows][AUXF]
+  uint32_t* ab;  // [NGS][GB][T + 2 kPadRows][16 lanes][NSP] packed chain states + lane scales
 };
 
 int launch_pipe_ns2(const Problem& p, const PipeCfg& cfg, cudaStream_t stream);
@@ -94,6 +92,7 @@ using namespace stream;
 
 constexpr int kSent = -(1 << 28);  // "no exponent": an all-zero lane
 constexpr int kRB = 8;             // chain steps between two rescales
+constexpr int kPadRows = 16;       // padding rows before and after every aux / stored-state tile (chain prefetch)
 
 // exact 2^e; 0 below the normal range, 2^1023 above
 __device__ __forceinline__ double pow2z(int e) {
@@ -133,40 +132,77 @@ struct CG {
   static constexpr int DEC = NS == 2 ? 208 : NS == 4 ? 420 : 850;
 };
 
+// Predicated vector loads / stores through L2 (ld/st.global.cg): the destination registers are zeroed and then
+// loaded under a predicate, in straight-line code, so that a load can stay in flight for many chain steps (a
+// branch or a select around the load would make the consumer wait for it at once).
+__device__ __forceinline__ void ldcg2f(const float* p, bool pred, float& a, float& b) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@q ld.global.cg.v2.f32 {%0, %1}, [%2];\n\t}"
+      : "=f"(a), "=f"(b)
+      : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldcg4f(const float* p, bool pred, float& a, float& b, float& c, float& d) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t@q ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(a), "=f"(b), "=f"(c), "=f"(d)
+      : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldcg2d(const double* p, bool pred, double& a, double& b) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+      "@q ld.global.cg.v2.f64 {%0, %1}, [%2];\n\t}"
+      : "=d"(a), "=d"(b)
+      : "l"(p), "r"((int)pred));
+}
+// keeps the old value when the predicate is false
+__device__ __forceinline__ void ldcg1i_keep(const int* p, bool pred, int& a) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.cg.s32 %0, [%1];\n\t}" : "+r"(a) : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void stcg2f(float* p, bool pred, float a, float b) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.cg.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(a), "f"(b), "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void stcg4f(float* p, bool pred, float a, float b, float c, float d) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a), "f"(b),
+               "f"(c), "f"(d), "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void stcg2d(double* p, bool pred, double a, double b) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.cg.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p), "d"(a), "d"(b), "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void stcg1i(int* p, bool pred, int a) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.global.cg.s32 [%0], %1;\n\t}" ::"l"(p), "r"(a), "r"((int)pred) : "memory");
+}
 template <int NS>
-__device__ __forceinline__ void ldcg_vec(const float* p, float (&v)[NS]) {
+__device__ __forceinline__ void ldcg_vec(const float* p, bool pred, float (&v)[NS]) {
   if constexpr (NS == 2) {
-    const float2 a = __ldcg(reinterpret_cast<const float2*>(p));
-    v[0] = a.x; v[1] = a.y;
+    ldcg2f(p, pred, v[0], v[1]);
   } else {
 #pragma unroll
-    for (int i = 0; i < NS; i += 4) {
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(p + i));
-      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
-    }
+    for (int i = 0; i < NS; i += 4) ldcg4f(p + i, pred, v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
 }
 template <int NS>
-__device__ __forceinline__ void stcg_vec(float* p, const float (&v)[NS]) {
+__device__ __forceinline__ void stcg_vec(float* p, bool pred, const float (&v)[NS]) {
   if constexpr (NS == 2) {
-    __stcg(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    stcg2f(p, pred, v[0], v[1]);
   } else {
 #pragma unroll
-    for (int i = 0; i < NS; i += 4) __stcg(reinterpret_cast<float4*>(p + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    for (int i = 0; i < NS; i += 4) stcg4f(p + i, pred, v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
 }
 template <int NS>
-__device__ __forceinline__ void ldcg_vec(const double* p, double (&v)[NS]) {
+__device__ __forceinline__ void ldcg_vec(const double* p, bool pred, double (&v)[NS]) {
 #pragma unroll
-  for (int i = 0; i < NS; i += 2) {
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(p + i));
-    v[i] = a.x; v[i + 1] = a.y;
-  }
+  for (int i = 0; i < NS; i += 2) ldcg2d(p + i, pred, v[i], v[i + 1]);
 }
 template <int NS>
-__device__ __forceinline__ void stcg_vec(double* p, const double (&v)[NS]) {
+__device__ __forceinline__ void stcg_vec(double* p, bool pred, const double (&v)[NS]) {
 #pragma unroll
-  for (int i = 0; i < NS; i += 2) __stcg(reinterpret_cast<double2*>(p + i), make_double2(v[i], v[i + 1]));
+  for (int i = 0; i < NS; i += 2) stcg2d(p + i, pred, v[i], v[i + 1]);
 }
 
 // x(s) <- (x(s) + x(s-1)) p(s) in the lane's position order, as fma(x(s-1), p(s), x(s) p(s)): the dependent path
@@ -223,25 +259,322 @@ __device__ __forceinline__ void block_entry(double (&x)[NS], int& e, double& fac
 }
 
 struct ChainArgs {
-  float* paux;      // emissions / gammas of this sequence at t = 0: + t*pstride + state
+  float* paux;      // emissions / gammas of this sequence at t = 0: + t*pstride + state (kPadRows rows of padding
+                    // before t = 0 and after t = T-1: prefetches beyond the sequence stay inside the tile)
   int64_t pstride;  // floats between time steps
-  double* ab;       // [T][Lpad] stored states, in the storing lane's position order
-  int* ex;          // [2][nblk][16] lane scales of the first half, per block of 8 steps
-  int nblk;
+  uint32_t* ab;     // stored states at t = 0: + t*16*NSP; a row = 16 lanes x {NS packed states, lane scale, padding}
   int Tb, Lb;
   float wgt;
   int want_grad;
   float* loss_out;
+  uint32_t ring;    // shared-memory ring of this warp (byte address in the shared window)
+};
+
+// Stored chain states: a non-negative double as 32 bits = 11-bit exponent + 21-bit mantissa (round to nearest).
+// gamma only needs ~1e-7 relative accuracy of the stored factor; the recursions themselves stay in float64.
+__device__ __forceinline__ uint32_t pack_state(double x) {
+  return (uint32_t)((unsigned long long)(__double_as_longlong(x) + (1ll << 30)) >> 31);
+}
+__device__ __forceinline__ double unpack_state(uint32_t u) { return __longlong_as_double((long long)((unsigned long long)u << 31)); }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NS>
+struct CRing {
+  static constexpr int NSP = NS + (NS == 2 ? 2 : 4);      // uint32 per lane and step of stored state: states, scale, padding
+  static constexpr int PB = NS * 4, OB = NSP * 4;         // bytes per lane and step: emissions, stored state
+  static constexpr int STEP = 32 * (PB + OB);             // ring bytes per step
+  static constexpr int U = NS == 2 ? 12 : NS == 4 ? 8 : NS == 8 ? 5 : 3;  // steps in flight
+  static constexpr int BYTES = U * STEP;
+};
+constexpr int pipe_chain_ring_bytes(int ns) {
+  return ns == 2 ? CRing<2>::BYTES : ns == 4 ? CRing<4>::BYTES : ns == 8 ? CRing<8>::BYTES : CRing<16>::BYTES;
+}
+
+// One sequence on one warp.  Iteration k of the FIRST half: alpha (lanes 0-15) at t = k, beta (lanes 16-31) at
+// t = T_b-1-k+odd; both store their state and lane scale.  Iteration k of the SECOND half: beta at t = Ha-1-k, alpha
+// at t = Ha+k; gamma_t = (sum of the fresh direction before its step) * (state the other direction stored at t) / Z.
+// T_b odd: the beta direction starts with a virtual step at t = T_b whose emission is 1 at the start state, which
+// leaves the start vector unchanged; the alpha direction's last iteration then has nothing to do.
+// Every lane fetches its own emissions and stored states with cp.async into a shared-memory ring, U steps ahead
+// (cp.async.wait_group keeps exactly U-1 steps in flight, which register prefetching cannot: the hardware has six
+// scoreboards); the copies are unconditional -- padding rows keep the addresses valid -- and stores are predicated,
+// so a body of 8 steps is branch-free.
+template <int NS>
+struct ChainRun {
+  using G = CG<NS>;
+  using RG = CRing<NS>;
+  static constexpr int Lpad = G::Lpad, U = RG::U, NSP = RG::NSP;
+  static constexpr int UB = kRB;              // steps per body
+  static constexpr int ABS = 16 * NSP;        // uint32 per row of stored states
+  const ChainArgs& a;
+  const int lane, hl;
+  const bool isb;
+  int Ha, odd;
+  bool live;
+  unsigned smask;
+  double x[NS], sum[NS];
+  int e;
+  double fac;
+  int64_t pstep, abstep;
+  const float* pld;
+  const uint32_t* old_;
+  float* gst;
+  uint32_t* abw;
+  uint32_t slot_addr, ring_lo, ring_hi;  // ring position of the step that is consumed / refilled next
+  int Ez;
+  double zinv;
+
+  __device__ __forceinline__ ChainRun(const ChainArgs& a_, int lane_) : a(a_), lane(lane_), hl(lane_ & 15), isb(lane_ >= 16) {}
+
+  __device__ __forceinline__ void advance_slot() {
+    slot_addr += RG::STEP;
+    if (slot_addr == ring_hi) slot_addr = ring_lo;
+  }
+  // this lane's emissions of the next step to fetch -> ring slot at `dst`
+  __device__ __forceinline__ void fetch_p(uint32_t dst) {
+    if constexpr (NS == 2) {
+      cp_async<8>(dst + lane * RG::PB, pld);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; i += 4) cp_async<16>(dst + lane * RG::PB + i * 4, pld + i);
+    }
+    pld += pstep;
+  }
+  __device__ __forceinline__ void fetch_o(uint32_t dst) {
+#pragma unroll
+    for (int i = 0; i < NSP; i += 4) cp_async<16>(dst + 32 * RG::PB + lane * RG::OB + i * 4, old_ + i);
+    old_ += abstep;
+  }
+  // emissions of the current slot in the lane's position order; lanes without a state hold zeros
+  __device__ __forceinline__ void read_p(double (&p)[NS]) const {
+    float raw[NS];
+    const uint32_t src = slot_addr + lane * RG::PB;
+    if constexpr (NS == 2) {
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(raw[0]), "=f"(raw[1]) : "r"(src));
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; i += 4)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(raw[i]), "=f"(raw[i + 1]), "=f"(raw[i + 2]), "=f"(raw[i + 3]) : "r"(src + i * 4));
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) p[j] = live ? (double)(isb ? raw[NS - 1 - j] : raw[j]) : 0.0;
+  }
+  // stored states of the other direction (its lane 15-hl holds this lane's states in reversed order) and its scale
+  __device__ __forceinline__ void read_o(double (&o)[NS], int& eo) const {
+    uint32_t v[NSP];
+    const uint32_t src = slot_addr + 32 * RG::PB + lane * RG::OB;
+#pragma unroll
+    for (int i = 0; i < NSP; i += 4)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i]), "=r"(v[i + 1]), "=r"(v[i + 2]), "=r"(v[i + 3]) : "r"(src + i * 4));
+#pragma unroll
+    for (int q = 0; q < NS; ++q) o[q] = live ? unpack_state(v[NS - 1 - q]) : 0.0;
+    eo = (int)v[NS];
+  }
+  __device__ __forceinline__ void store_state(bool ok) {
+    uint32_t v[NSP];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) v[q] = pack_state(x[q]);
+    v[NS] = (uint32_t)e;
+#pragma unroll
+    for (int q = NS + 1; q < NSP; ++q) v[q] = 0u;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NSP; i += 4) __stcg(reinterpret_cast<uint4*>(abw + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    }
+    abw += abstep;
+  }
+
+  // ------------------------------------------------------------------ first half
+  template <bool kFirst, bool kTail>
+  __device__ __forceinline__ void body1(int base) {
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int k = base + j;
+      if (j == 0) block_entry<NS>(x, e, fac, hl);
+      double p[NS];
+      cp_async_wait<U - 1>();
+      read_p(p);
+      fetch_p(slot_addr);
+      cp_async_commit();
+      advance_slot();
+      bool st_ok = live;
+      if (kFirst && j == 0) {
+        // first step of alpha; first step of beta (T_b even) or its virtual step (T_b odd)
+        const bool virt = isb && odd;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) p[q] = ((smask >> q) & 1u) ? (virt ? 1.0 : p[q]) : 0.0;
+        st_ok = live && !virt;
+      }
+      if (kFirst && j == 1) {
+        const bool first_beta = isb && odd;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) p[q] = (!first_beta || ((smask >> q) & 1u)) ? p[q] : 0.0;
+      }
+      if (kTail) {
+        const bool act = k < Ha;
+        double xs[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) xs[q] = x[q];
+        chain_step<NS, false>(x, sum, p, fac);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) x[q] = act ? x[q] : xs[q];
+        st_ok = st_ok && act;
+      } else {
+        chain_step<NS, false>(x, sum, p, fac);
+      }
+      store_state(st_ok);
+    }
+  }
+
+  // ------------------------------------------------------------------ second half
+  template <bool kTail>
+  __device__ __forceinline__ void body2(int base) {
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int k = base + j;
+      if (j == 0 && base > 0) block_entry<NS>(x, e, fac, hl);
+      double p[NS], o[NS];
+      int eo;
+      cp_async_wait<U - 1>();
+      read_p(p);
+      read_o(o, eo);
+      fetch_p(slot_addr);
+      fetch_o(slot_addr);
+      cp_async_commit();
+      advance_slot();
+      // gamma = sum * stored * 2^(e + eo - Ez) / zhat; the power of two is split over both factors (range)
+      const int dd = e + eo - Ez;
+      const double sA = pow2z(dd >> 1), sB = pow2z(dd - (dd >> 1)) * zinv;
+      chain_step<NS, true>(x, sum, p, fac);
+      float g[NS], gm[NS];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) g[q] = (float)((sum[q] * sA) * (o[q] * sB));
+#pragma unroll
+      for (int q = 0; q < NS; ++q) gm[q] = isb ? g[NS - 1 - q] : g[q];
+      // (alpha's last iteration is beyond T_b when T_b is odd)
+      stcg_vec<NS>(gst, live && (!kTail || k < Ha) && (isb || k < Ha - odd), gm);
+      gst += pstep;
+    }
+  }
+
+  __device__ __forceinline__ void run() {
+    const int Tb = a.Tb, Lb = a.Lb;
+    Ha = (Tb + 1) >> 1;
+    odd = Tb & 1;
+    // position q = hl*NS + j of a direction is state q for alpha and state Lpad-1-q for beta: both shift the same way
+    const int soff = isb ? Lpad - NS - hl * NS : hl * NS;  // the lane's states in memory order start here
+    live = soff < Lb;  // (stage A wrote p = 0 for the padded states of a live lane)
+    smask = 0;         // bit j: state is the direction's start state
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int sj = isb ? Lpad - 1 - (hl * NS + j) : hl * NS + j;
+      if (sj == (isb ? Lb - 1 : 0)) smask |= 1u << j;
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) x[j] = ((smask >> j) & 1u) ? 1.0 : 0.0;
+    e = 0;
+    fac = hl == 0 ? 0.0 : 1.0;
+    pstep = isb ? -a.pstride : a.pstride;  // alpha walks up in time, beta walks down (both halves)
+    abstep = isb ? -(int64_t)ABS : (int64_t)ABS;
+    ring_lo = a.ring;
+    ring_hi = a.ring + RG::BYTES;
+    slot_addr = ring_lo;
+
+    // ---- first half (beta's iteration 0 is virtual when T_b is odd: its row T_b is padding or unused)
+    const int t1_0 = isb ? Tb - 1 + odd : 0;
+    pld = a.paux + soff + (int64_t)t1_0 * a.pstride;
+    for (int j = 0; j < U; ++j) {
+      fetch_p(ring_lo + j * RG::STEP);
+      cp_async_commit();
+    }
+    abw = a.ab + (int64_t)t1_0 * ABS + hl * NSP;
+    {
+      int base = 0;
+      if (UB <= Ha) {
+        body1<true, false>(0);
+        for (base = UB; base + UB <= Ha; base += UB) body1<false, false>(base);
+        if (base < Ha) body1<false, true>(base);
+      } else {
+        body1<true, true>(0);
+      }
+    }
+    cp_async_wait<0>();
+    __syncwarp();  // the other half-warp's stores are visible to this lane's copies below
+
+    // ---- second half
+    const int t2_0 = isb ? Ha - 1 : Ha;
+    old_ = a.ab + (int64_t)t2_0 * ABS + (15 - hl) * NSP;
+    pld = a.paux + soff + (int64_t)t2_0 * a.pstride;
+    gst = const_cast<float*>(pld);  // gamma' overwrites the emissions of the same time step
+    slot_addr = ring_lo;
+    for (int j = 0; j < U; ++j) {
+      fetch_p(ring_lo + j * RG::STEP);
+      fetch_o(ring_lo + j * RG::STEP);
+      cp_async_commit();
+    }
+
+    block_entry<NS>(x, e, fac, hl);
+    // ---- Z = sum_s alpha_t(s) beta_t(s) at t = Ha-1 (beta lanes): beta_t(s) = sum of the beta direction's next step
+    {
+      const double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
+#pragma unroll
+      for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
+      sum[0] = fma(up, fac, x[0]);
+      double o[NS];
+      int eo0;
+      cp_async_wait<U - 1>();
+      read_o(o, eo0);
+      const int ms = top_exponent<NS>(sum), mo = top_exponent<NS>(o);
+      double part = 0.0;
+      int ep = kSent;
+      if (ms != kSent && mo != kSent) {
+        const double s1 = pow2z(-ms), s2 = pow2z(-mo);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) part = fma(sum[j] * s1, o[j] * s2, part);
+        if (part > 0.0) ep = e + eo0 + ms + mo;
+      }
+      int emax = ep;
+#pragma unroll
+      for (int o2 = 8; o2 > 0; o2 >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o2, 16));
+      part = ep == kSent ? 0.0 : part * pow2z(ep - emax);
+#pragma unroll
+      for (int o2 = 8; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2, 16);
+      const double zsum = __shfl_sync(0xffffffffu, part, 16);
+      emax = __shfl_sync(0xffffffffu, emax, 16);
+      const int ezf = __double2hiint(zsum) >> 20;
+      const bool writer = hl == 0 && !isb;
+      if (emax == kSent || !(zsum > 0.0) || ezf <= 0 || ezf >= 0x7ff) {
+        if (writer) *a.loss_out = INFINITY;
+        zinv = 0.0;
+        Ez = 0;
+      } else {
+        const int ezz = ezf - 1023;
+        const double zhat = zsum * pow2z(-ezz);
+        Ez = emax + ezz;
+        if (writer) *a.loss_out = (float)(-(log(zhat) + (double)Ez * 0.6931471805599453));
+        zinv = -(double)a.wgt / zhat;  // negative: stage C ADDS gamma' = -w*gamma to w*softmax
+      }
+    }
+    if (a.want_grad) {
+      int base = 0;
+      for (; base + UB <= Ha; base += UB) body2<false>(base);
+      if (base < Ha) body2<true>(base);
+    }
+    cp_async_wait<0>();  // nothing may land in the ring after the next sequence has started
+  }
 };
 
 template <int NS>
 __device__ __forceinline__ void chain_sequence(const ChainArgs& a, const int lane) {
-  using G = CG<NS>;
-  constexpr int Lpad = G::Lpad, U = G::U, UO = G::UO;
-  const int hl = lane & 15;
-  const bool isb = lane >= 16;
-  const int Tb = a.Tb, Lb = a.Lb;
-  if (Tb == 1) {  // one frame, one state: gamma = 1
+  if (a.Tb == 1) {  // one frame, one state: gamma = 1
     if (lane == 0) {
       const float p0 = __ldcg(a.paux);
       *a.loss_out = -logf(p0);
@@ -249,195 +582,8 @@ __device__ __forceinline__ void chain_sequence(const ChainArgs& a, const int lan
     }
     return;
   }
-  const int Ha = (Tb + 1) >> 1, odd = Tb & 1;
-  // position q = hl*NS + j of a direction is state q for alpha and state Lpad-1-q for beta: both shift the same way
-  const int soff = isb ? Lpad - NS - hl * NS : hl * NS;  // the lane's states in memory order start here
-  const bool live = soff < Lb;
-  unsigned vmask = 0, smask = 0;  // bit j: state exists; state is the direction's start state
-#pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    const int sj = isb ? Lpad - 1 - (hl * NS + j) : hl * NS + j;
-    if (sj < Lb) vmask |= 1u << j;
-    if (sj == (isb ? Lb - 1 : 0)) smask |= 1u << j;
-  }
-  double x[NS], sum[NS];
-#pragma unroll
-  for (int j = 0; j < NS; ++j) x[j] = ((smask >> j) & 1u) ? 1.0 : 0.0;
-  int e = 0;
-  double fac = hl == 0 ? 0.0 : 1.0;
-  const float* prow = a.paux + soff;
-  const int dirx = isb ? 1 : 0;
-
-  // raw emissions (memory order) -> the lane's position order, padded states and (first step) non-start states zeroed
-  auto to_p = [&](const float (&raw)[NS], double (&p)[NS], bool start_only) {
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const float v = isb ? raw[NS - 1 - j] : raw[j];
-      const bool keep = ((vmask >> j) & 1u) && (!start_only || ((smask >> j) & 1u));
-      p[j] = keep ? (double)v : 0.0;
-    }
-  };
-  auto load_raw = [&](int t, bool ok, float (&raw)[NS]) {
-    if (ok && live) {
-      ldcg_vec<NS>(prow + (int64_t)t * a.pstride, raw);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) raw[j] = 0.f;
-    }
-  };
-
-  // ------------------------------------------------------------------ first half: iteration k, alpha at t = k,
-  // beta at t = T_b-1-k+odd (idle at k = 0 when T_b is odd)
-  auto t1 = [&](int k) { return isb ? Tb - 1 - k + odd : k; };
-  auto ok1 = [&](int k) { return k < Ha && (!isb || k >= odd); };
-  float pq[U][NS];
-#pragma unroll
-  for (int j = 0; j < U; ++j) load_raw(t1(j), ok1(j), pq[j]);
-  int* exw = a.ex + dirx * a.nblk * 16 + hl;
-  for (int base = 0; base < Ha; base += U) {
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int k = base + j;
-      if (k < Ha) {
-        if ((k & (kRB - 1)) == 0) {
-          block_entry<NS>(x, e, fac, hl);
-          if (live) __stcg(exw + (k >> 3) * 16, e);
-        }
-        double p[NS];
-        const bool special = j < 2 && base == 0;  // the first valid step of a direction is k = 0 (alpha) or k = odd (beta)
-        to_p(pq[j], p, special && k == (isb ? odd : 0));
-        load_raw(t1(k + U), ok1(k + U), pq[j]);
-        const bool valid = !(special && k == 0 && isb && odd);
-        if (special && k == 0) {
-          double xs[NS];
-#pragma unroll
-          for (int q = 0; q < NS; ++q) xs[q] = x[q];
-          chain_step<NS, false>(x, sum, p, fac);
-#pragma unroll
-          for (int q = 0; q < NS; ++q) x[q] = valid ? x[q] : xs[q];
-        } else {
-          chain_step<NS, false>(x, sum, p, fac);
-        }
-        if (live && valid) stcg_vec<NS>(a.ab + (int64_t)t1(k) * Lpad + hl * NS, x);
-      }
-    }
-  }
-  __syncwarp();  // the other half-warp's stores are visible to this lane's loads below
-
-  // ------------------------------------------------------------------ second half: iteration k, beta at
-  // t = Ha-1-k, alpha at t = Ha+k-odd (idle at k = 0 when T_b is odd).  kp = the iteration at which the other
-  // direction stored its state of time t.
-  auto t2 = [&](int k) { return isb ? Ha - 1 - k : Ha + k - odd; };
-  auto ok2 = [&](int k) { return k < Ha && (isb || k >= odd); };
-  const double* orow = a.ab + (15 - hl) * NS;
-  const int* exr = a.ex + (1 - dirx) * a.nblk * 16 + (15 - hl);
-  double oq[UO][NS];
-  auto load_o = [&](int t, bool ok, double (&o)[NS]) {
-    if (ok && live) {
-      ldcg_vec<NS>(orow + (int64_t)t * Lpad, o);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) o[j] = 0.0;
-    }
-  };
-#pragma unroll
-  for (int j = 0; j < U; ++j) load_raw(t2(j), ok2(j), pq[j]);
-#pragma unroll
-  for (int j = 0; j < UO; ++j) load_o(t2(j), ok2(j), oq[j]);
-  const int kp0 = isb ? Ha - 1 : Ha - 1 + odd;
-  const int nb1 = (Ha + kRB - 1) >> 3;  // blocks the first half stored
-  int eo = live ? __ldcg(exr + min(kp0 >> 3, nb1 - 1) * 16) : 0;
-  int eo_nxt = (live && (kp0 >> 3) >= 1) ? __ldcg(exr + ((kp0 >> 3) - 1) * 16) : 0;
-
-  block_entry<NS>(x, e, fac, hl);
-  // ---- Z = sum_s alpha_t(s) beta_t(s) at t = Ha-1 (beta lanes): beta_t(s) = sum of the beta direction's next step
-  double zinv;
-  int Ez;
-  {
-    const double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, 16);
-#pragma unroll
-    for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
-    sum[0] = fma(up, fac, x[0]);
-    double o[NS];
-#pragma unroll
-    for (int j = 0; j < NS; ++j) o[j] = oq[0][NS - 1 - j];
-    const int ms = top_exponent<NS>(sum), mo = top_exponent<NS>(o);
-    double part = 0.0;
-    int ep = kSent;
-    if (ms != kSent && mo != kSent) {
-      const double s1 = pow2z(-ms), s2 = pow2z(-mo);
-#pragma unroll
-      for (int j = 0; j < NS; ++j) part = fma(sum[j] * s1, o[j] * s2, part);
-      if (part > 0.0) ep = e + eo + ms + mo;
-    }
-    int emax = ep;
-#pragma unroll
-    for (int o2 = 8; o2 > 0; o2 >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o2, 16));
-    part = ep == kSent ? 0.0 : part * pow2z(ep - emax);
-#pragma unroll
-    for (int o2 = 8; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2, 16);
-    const double zsum = __shfl_sync(0xffffffffu, part, 16);
-    emax = __shfl_sync(0xffffffffu, emax, 16);
-    const int ezf = __double2hiint(zsum) >> 20;
-    if (emax == kSent || !(zsum > 0.0) || ezf <= 0 || ezf >= 0x7ff) {
-      if (lane == 0) *a.loss_out = INFINITY;
-      zinv = 0.0;
-      Ez = 0;
-    } else {
-      const int ezz = ezf - 1023;
-      const double zhat = zsum * pow2z(-ezz);
-      Ez = emax + ezz;
-      if (lane == 0) *a.loss_out = (float)(-(log(zhat) + (double)Ez * 0.6931471805599453));
-      zinv = -(double)a.wgt / zhat;  // negative: stage C ADDS gamma' = -w*gamma to w*softmax
-    }
-  }
-  if (!a.want_grad) return;
-
-  float* grow = a.paux + soff;
-  int kp = kp0;
-  for (int base = 0; base < Ha; base += U) {
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int k = base + j;
-      if (k < Ha) {
-        if ((k & (kRB - 1)) == 0 && k > 0) block_entry<NS>(x, e, fac, hl);
-        if (k > 0) {
-          --kp;
-          if ((kp & 7) == 7) {  // the other direction's block of 8 steps changes
-            eo = eo_nxt;
-            eo_nxt = (live && (kp >> 3) >= 1) ? __ldcg(exr + ((kp >> 3) - 1) * 16) : 0;
-          }
-        }
-        double p[NS], o[NS];
-        to_p(pq[j], p, false);
-        load_raw(t2(k + U), ok2(k + U), pq[j]);
-#pragma unroll
-        for (int q = 0; q < NS; ++q) o[q] = oq[j % UO][NS - 1 - q];
-        load_o(t2(k + UO), ok2(k + UO), oq[j % UO]);
-        // gamma = sum * stored * 2^(e + eo - Ez) / zhat; the power of two is split over both factors (range)
-        const int dd = e + eo - Ez;
-        const double sA = pow2z(dd >> 1), sB = pow2z(dd - (dd >> 1)) * zinv;
-        const bool special = j == 0 && base == 0;
-        const bool valid = !(special && !isb && odd);
-        if (special) {
-          double xs[NS];
-#pragma unroll
-          for (int q = 0; q < NS; ++q) xs[q] = x[q];
-          chain_step<NS, true>(x, sum, p, fac);
-#pragma unroll
-          for (int q = 0; q < NS; ++q) x[q] = valid ? x[q] : xs[q];
-        } else {
-          chain_step<NS, true>(x, sum, p, fac);
-        }
-        float g[NS], gm[NS];
-#pragma unroll
-        for (int q = 0; q < NS; ++q) g[q] = (float)((sum[q] * sA) * (o[q] * sB));
-#pragma unroll
-        for (int q = 0; q < NS; ++q) gm[q] = isb ? g[NS - 1 - q] : g[q];
-        if (live && valid) stcg_vec<NS>(grow + (int64_t)t2(k) * a.pstride, gm);
-      }
-    }
-  }
+  ChainRun<NS> r(a, lane);
+  r.run();
 }
 
 // ============================================================================ stages A and C: row warp
@@ -470,15 +616,16 @@ struct PRows {
     gbytes = (uint32_t)gcnt * (uint32_t)C * 4u;
     ph_fixed = (((unsigned)P.B * (unsigned)C) & 3u) == 0 ? (int)((((unsigned)b0 & 3u) * ((unsigned)C & 3u)) & 3u) : -1;
   }
-  // + per-sequence state of the consumer (lengths, weight, labels of this lane's states)
-  __device__ __forceinline__ void begin_task(int g) {
+  // + per-sequence state of the consumer (lengths, weight, labels of this lane's states) from the slot's label buffer:
+  // [GB][Lpad] labels, then [GB] headers
+  __device__ __forceinline__ void begin_task(int g, const unsigned char* lbuf) {
     set_group(g);
     Tb = 0; Lb = 0; max_rank = 0; wgt = 0.f;
     if (seq < gcnt) {
-      const int4 h = cfg.hdr[b0 + seq];
+      const int4 h = *reinterpret_cast<const int4*>(lbuf + GB * Lpad * 4 + seq * 16);
       Tb = h.x; Lb = h.y; max_rank = h.z; wgt = __int_as_float(h.w);
     }
-    const int* lab_seq = cfg.lab + (b0 + min(seq, gcnt - 1)) * Lpad;
+    const int* lab_seq = reinterpret_cast<const int*>(lbuf) + seq * Lpad;
 #pragma unroll
     for (int j = 0; j < NSL; ++j) {
       const int st = li + j * LPR;
@@ -625,9 +772,14 @@ struct PRows {
         const int l = labr[j];
         xv[j] = yr[l >= 0 ? (l & kLabMask) : 0];
       }
+      // states L_b .. roundup(L_b, NS)-1 share a chain lane with real states: their emission is 0
+      const int Lz = (Lb + NS - 1) / NS * NS;
 #pragma unroll
-      for (int j = 0; j < NSL; ++j)
-        if (labr[j] >= 0) __stcg(arow + li + j * LPR, fmaxf(ex2f(fmaf(xv[j], kLog2e, -mb)) * rs, kPMin));
+      for (int j = 0; j < NSL; ++j) {
+        const int st = li + j * LPR;
+        if (labr[j] >= 0) __stcg(arow + st, fmaxf(ex2f(fmaf(xv[j], kLog2e, -mb)) * rs, kPMin));
+        else if (st >= Lb && st < Lz) __stcg(arow + st, 0.f);
+      }
     }
   }
 
@@ -685,108 +837,143 @@ struct PRows {
 };
 
 // meta word of a ring slot
-constexpr int kMetaA = 1, kMetaC = 2, kMetaLast = 8;
+constexpr int kMetaA = 1, kMetaC = 2, kMetaFirst = 4, kMetaLast = 8;
 
+// Row tickets are handed out statically: CTA c owns tickets c, c + grid, c + 2 grid, ...; a ticket is a task (group,
+// block of TB = KS*NRW time steps) and row warp w owns its time steps w, w + NRW, ...  Every row warp walks its CTA's
+// sequence twice, without talking to the other warps: position ka = next stage-A task, kc <= ka = next stage-C
+// task.  Stage C goes first whenever the chains of its group are done; otherwise stage A runs ahead, at most `wmax`
+// positions: the window between the stages adapts to the chain latency, and it bounds the L2 footprint (the tickets
+// in flight span grid*TB slabs per stage plus the window).  Every dependency of a task belongs to tasks at earlier
+// positions: no deadlock once every CTA of the grid has started.
 template <int NS, int LPR, int CPL>
 __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& cfg, unsigned char* smem_raw, int rw, int lane) {
   using R = PRows<NS, LPR, CPL>;
-  constexpr int GB = R::GB;
-  const int D = cfg.D;
+  constexpr int GB = R::GB, Lpad = R::Lpad;
+  const int D = cfg.D, NRW = cfg.NRW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar) + rw * D;
   int4* meta = reinterpret_cast<int4*>(smem_raw + cfg.o_meta) + rw * D;
+  volatile int* flags = reinterpret_cast<volatile int*>(smem_raw + cfg.o_flags);  // dependencies known to be met
   unsigned char* ring = smem_raw + cfg.o_ring + (size_t)rw * D * cfg.SLOTB;
   R prod(P, cfg, lane), cons(P, cfg, lane);
   const bool do_a = cfg.phase_mask & 1, do_c = (cfg.phase_mask & 4) && cfg.want_grad;
   const int NA = cfg.NG * cfg.TPG;
-  const int NTK = do_c ? NA + cfg.lag : NA;
   const int T = (int)P.T;
+  const int G = (int)gridDim.x, c0 = (int)blockIdx.x;
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-  const size_t aux_row_bytes = (size_t)cfg.AUXF * 4;
+  const uint32_t aux_row_bytes = (uint32_t)cfg.AUXF * 4u;
 
   // producer cursor (warp-uniform)
-  int cur_type = 0, cur_gi = 0, cur_t = 0, cur_tend = 0;
-  int pend_c = -1;   // stage-C task of the current ticket, not started yet
-  int pend_a = -1;   // stage-A task of the current ticket, waiting for its aux slot
-  bool exhausted = false;
-  int head = 0, tail = 0, inflight = 0;
+  int cur_type = 0, cur_gi = 0, cur_t = 0, cur_tend = 0, cur_first = 0, cur_cnt = 0;
+  int ka = 0, kc = 0;
+  bool finished = false;
+  int head = 0, tail = 0, inflight = 0, attempts = 0;
   uint32_t par = 0;
-  int cons_gi = -1, cons_type = 0;
 
-  auto aux_row = [&](int gi, int t) { return cfg.aux + ((size_t)(gi % cfg.NGS) * T + t) * cfg.AUXF; };
-  auto signal = [&](int* ctr) {
-    __syncwarp();
-    if (lane == 0) red_release_add(ctr, 1);
-  };
-  auto poll_ge = [&](const int* ctr, int want) {
+  auto aux_row = [&](int gi, int t) { return cfg.aux + ((size_t)(gi % cfg.NGS) * (T + 2 * kPadRows) + kPadRows + t) * cfg.AUXF; };
+  // Dependency `which` (0: the chains of a stage-C task's group, 1: the aux slot of a stage-A task) of position k.
+  // All row warps of the CTA wait for the same things in the same order: what one of them has seen is cached in shared
+  // memory, and only warp k % NRW polls the global counter at full rate.
+  auto dep_ready = [&](int which, int k, const int* ctr, int want) -> bool {
+    if (k < flags[which]) {
+      __threadfence_block();
+      return true;
+    }
+    if ((k % NRW) != rw && ((++attempts) & 7) != 0) return false;
     int ok = 0;
     if (lane == 0) ok = ld_acquire(ctr) >= want;
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    __threadfence_block();
+    if (lane == 0) atomicMax(const_cast<int*>(&flags[which]), k + 1);
+    return true;
+  };
+  // labels + sequence headers of group gi -> label buffer of a slot (16-byte async copies, one commit group)
+  auto prefetch_labels = [&](int gi, unsigned char* slot) {
+    const int64_t b0 = (int64_t)gi * GB;
+    const int gcnt = (int)min((int64_t)GB, P.B - b0);
+    unsigned char* lb = slot + cfg.RSg + aux_row_bytes;
+    const int nlab = gcnt * (Lpad / 4);
+    const char* src = reinterpret_cast<const char*>(cfg.lab + b0 * Lpad);
+    for (int c = lane; c < nlab; c += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + c * 16)), "l"(src + (size_t)c * 16) : "memory");
+    if (lane < gcnt)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + GB * Lpad * 4 + lane * 16)),
+                   "l"(reinterpret_cast<const char*>(cfg.hdr + b0) + lane * 16)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   // returns 1 if a load was issued, 0 if the producer has to wait (or is done)
   auto try_produce = [&]() -> int {
     for (;;) {
       if (cur_type == 0) {
-        if (pend_a >= 0) {
-          const int gi = pend_a / cfg.TPG, tb = pend_a - gi * cfg.TPG;
-          // the aux slot of this group was used by group gi - NGS: its last reader must be done
-          if (gi >= cfg.NGS) {
-            const int gp = gi - cfg.NGS;
-            const bool free_ = do_c ? poll_ge(cfg.doneC + gp, cfg.TPG) : poll_ge(cfg.doneB + gp, __ldg(&cfg.grp[gp].y));
-            if (!free_) return 0;
-          }
-          pend_a = -1;
-          const int Tg = __ldg(&cfg.grp[gi].x);
-          const int t0 = tb * cfg.TB, t1 = min(min(T, t0 + cfg.TB), Tg);
-          if (t1 <= t0) {
-            signal(cfg.doneA + gi);
-            continue;
-          }
-          cur_type = kMetaA; cur_gi = gi; cur_t = t0; cur_tend = t1;
-          prod.set_group(gi);
-        } else if (pend_c >= 0) {
-          const int gi = pend_c / cfg.TPG, tb = pend_c - gi * cfg.TPG;
-          if (!poll_ge(cfg.doneB + gi, __ldg(&cfg.grp[gi].y))) return 0;  // the group's chains
-          fence_proxy_async_all();  // gamma' and row statistics were written through the generic proxy
-          pend_c = -1;
-          const int Tg = __ldg(&cfg.grp[gi].x);
-          const int t0 = tb * cfg.TB, t1 = min(T, t0 + cfg.TB), tl = min(t1, Tg);
-          prod.set_group(gi);
-          // rows beyond the group's longest input: zeros, written directly (ragged batches only)
-          for (int t = max(t0, Tg); t < t1; ++t) {
-            float* dst = P.grad + ((int64_t)t * P.B + prod.b0) * P.C;
-            const int n = prod.gcnt * (int)P.C;
-            for (int c = lane; c < n; c += 32) dst[c] = 0.f;
-          }
-          if (tl <= t0) {
-            signal(cfg.doneC + gi);
-            continue;
-          }
-          cur_type = kMetaC; cur_gi = gi; cur_t = t0; cur_tend = tl;
-        } else {
-          if (exhausted) return 0;
-          int n = 0;
-          if (lane == 0) n = atomicAdd(cfg.ctr, 1);
-          n = __shfl_sync(0xffffffffu, n, 0);
-          if (n >= NTK) {
-            exhausted = true;
-            return 0;
-          }
-          if (do_a && n < NA) pend_a = n;
-          if (do_c && n - cfg.lag >= 0 && n - cfg.lag < NA) pend_c = n - cfg.lag;
-          continue;
+        const int64_t na = (int64_t)c0 + (int64_t)ka * G, nc = (int64_t)c0 + (int64_t)kc * G;
+        const bool haveA = do_a && na < NA, haveC = do_c && nc < NA;
+        if (!haveA && !haveC) {
+          finished = true;
+          return 0;
         }
+        bool started = false;
+        if (haveC && (kc < ka || !haveA)) {
+          const int gi = (int)nc / cfg.TPG, tb = (int)nc - gi * cfg.TPG;
+          const int2 gg = __ldg(&cfg.grp[gi]);
+          if (dep_ready(0, kc, cfg.doneB + gi, gg.y)) {  // the group's chains
+            fence_proxy_async_all();  // gamma' and row statistics were written through the generic proxy
+            const int Tg = gg.x;
+            const int t0 = tb * cfg.TB + rw, t1 = min(T, (tb + 1) * cfg.TB), tl = min(t1, Tg);
+            prod.set_group(gi);
+            // rows beyond the group's longest input: zeros, written directly (ragged batches only)
+            for (int t = t0 + ((max(Tg - t0, 0) + NRW - 1) / NRW) * NRW; t < t1; t += NRW) {
+              float* dst = P.grad + ((int64_t)t * P.B + prod.b0) * P.C;
+              const int n = prod.gcnt * (int)P.C;
+              for (int c = lane; c < n; c += 32) dst[c] = 0.f;
+            }
+            if (t0 < tl) {
+              cur_type = kMetaC; cur_gi = gi; cur_t = t0; cur_tend = tl; cur_first = 1;
+              cur_cnt = (tl - t0 + NRW - 1) / NRW;
+            }
+            ++kc;
+            started = true;
+          }
+        }
+        if (!started && haveA && (!do_c || ka - kc < cfg.wmax)) {
+          const int gi = (int)na / cfg.TPG, tb = (int)na - gi * cfg.TPG;
+          bool ok = true;
+          if (gi >= cfg.NGS) {
+            // the aux slot of this group was used by group gi - NGS: its last reader must be done
+            const int gp = gi - cfg.NGS;
+            const int2 gg = __ldg(&cfg.grp[gp]);
+            ok = do_c ? dep_ready(1, ka, cfg.doneC + gp, gg.x) : dep_ready(1, ka, cfg.doneB + gp, gg.y);
+          }
+          if (ok) {
+            const int Tg = __ldg(&cfg.grp[gi].x);
+            const int t0 = tb * cfg.TB + rw, t1 = min(min(T, (tb + 1) * cfg.TB), Tg);
+            if (t0 < t1) {
+              cur_type = kMetaA; cur_gi = gi; cur_t = t0; cur_tend = t1; cur_first = 1;
+              cur_cnt = (t1 - t0 + NRW - 1) / NRW;
+              prod.set_group(gi);
+            }
+            ++ka;
+            started = true;
+          }
+        }
+        if (!started) return 0;
+        if (cur_type == 0) continue;  // nothing to do for this warp in that task
       }
       // issue the load of (cur_type, cur_gi, cur_t) into slot `head`
-      const int t = cur_t++;
-      const bool last = cur_t == cur_tend;
+      const int t = cur_t;
+      cur_t += NRW;
+      const bool last = cur_t >= cur_tend;
       unsigned char* slot = ring + (size_t)head * cfg.SLOTB;
+      if (cur_first) prefetch_labels(cur_gi, slot);
       if (lane == 0) {
-        meta[head] = make_int4(cur_type | (last ? kMetaLast : 0), t, cur_gi, 0);
+        meta[head] = make_int4(cur_type | (cur_first ? kMetaFirst : 0) | (last ? kMetaLast : 0), t, cur_gi, cur_cnt);
         if (cur_type == kMetaA) prod.issue_load(slot, &bars[head], t, pol_keep, nullptr, 0);
-        else prod.issue_load(slot, &bars[head], t, pol_stream, aux_row(cur_gi, t), (uint32_t)aux_row_bytes);
+        else prod.issue_load(slot, &bars[head], t, pol_stream, aux_row(cur_gi, t), aux_row_bytes);
       }
       __syncwarp();
+      cur_first = 0;
       if (last) cur_type = 0;
       head = head + 1 == D ? 0 : head + 1;
       ++inflight;
@@ -800,11 +987,11 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
       if (!try_produce()) break;
     }
     if (inflight == 0) {
-      if (exhausted && cur_type == 0 && pend_a < 0 && pend_c < 0) break;
+      if (finished) break;
       const unsigned long long now = gtime();
       if (t_idle == 0) t_idle = now;
-      else if (now - t_idle > 4000000000ull) wait_timeout("row warp dependency", pend_a, pend_c);
-      __nanosleep(128);
+      else if (now - t_idle > 4000000000ull) wait_timeout("row warp dependency", ka, kc);
+      __nanosleep(100);
       continue;
     }
     t_idle = 0;
@@ -814,24 +1001,28 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
     const int4 mt = meta[tail];
     unsigned char* slot = ring + (size_t)tail * cfg.SLOTB;
     const int type = mt.x & 3, t = mt.y, gi = mt.z;
-    if (gi != cons_gi || type != cons_type) {
-      cons.begin_task(gi);
-      cons_gi = gi;
-      cons_type = type;
+    if (mt.x & kMetaFirst) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      cons.begin_task(gi, slot + cfg.RSg + aux_row_bytes);
     }
     if (type == kMetaA) {
       cons.stage_a(t, slot, aux_row(gi, t));
       if (lane == 0) bulk_commit();  // one (empty) group per consumed slot keeps the wait below uniform
       if (mt.x & kMetaLast) {
         fence_proxy_async_all();
-        signal(cfg.doneA + gi);
+        __syncwarp();
+        if (lane == 0) red_release_add(cfg.doneA + gi, mt.w);
       }
     } else {
       cons.stage_c(t, slot, reinterpret_cast<const float*>(slot + cfg.RSg));
       fence_proxy_async();  // the slab is read by the async proxy (bulk store)
       __syncwarp();
       if (lane == 0) cons.issue_store(slot, t, pol_stream);
-      if (mt.x & kMetaLast) signal(cfg.doneC + gi);
+      if (mt.x & kMetaLast) {
+        __syncwarp();
+        if (lane == 0) red_release_add(cfg.doneC + gi, mt.w);
+      }
     }
     tail = tail + 1 == D ? 0 : tail + 1;
     --inflight;
@@ -843,7 +1034,7 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
 }
 
 template <int NS, int LPR>
-__device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg& cfg, int lane) {
+__device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg& cfg, int lane, uint32_t ring) {
   constexpr int GB = 32 / LPR, Lpad = 16 * NS;
   const int T = (int)P.T;
   for (;;) {
@@ -858,7 +1049,7 @@ __device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg&
       unsigned long long t0 = 0;
       for (;;) {
         int ok = 0;
-        if (lane == 0) ok = ld_acquire(cfg.doneA + gi) >= cfg.TPG;
+        if (lane == 0) ok = ld_acquire(cfg.doneA + gi) >= __ldg(&cfg.grp[gi].x);
         if (__shfl_sync(0xffffffffu, ok, 0)) break;
         const unsigned long long now = gtime();
         if (t0 == 0) t0 = now;
@@ -868,11 +1059,11 @@ __device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg&
       }
       ChainArgs a;
       const size_t slot = (size_t)(gi % cfg.NGS);
-      a.paux = cfg.aux + (slot * T) * cfg.AUXF + sq * Lpad;
+      const size_t TP = (size_t)T + 2 * kPadRows;
+      a.paux = cfg.aux + (slot * TP + kPadRows) * cfg.AUXF + sq * Lpad;
       a.pstride = cfg.AUXF;
-      a.ab = cfg.ab + ((slot * GB + sq) * (size_t)T) * Lpad;
-      a.ex = cfg.ex + ((slot * GB + sq) * 2) * (size_t)cfg.nblk * 16;
-      a.nblk = cfg.nblk;
+      a.ab = cfg.ab + ((slot * GB + sq) * TP + kPadRows) * (size_t)(16 * CRing<NS>::NSP);
+      a.ring = ring;
       a.Tb = h.x; a.Lb = h.y; a.wgt = __int_as_float(h.w);
       a.want_grad = cfg.want_grad;
       a.loss_out = P.loss + b;
@@ -889,6 +1080,7 @@ __global__ void __launch_bounds__(PipeTraits<NS>::kThreads, 1) nbctc_pipe_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + cfg.o_bar);
   for (int i = tid; i < cfg.NRW * cfg.D; i += blockDim.x) mbar_init(&bars[i], 1);
+  if (tid < 4) reinterpret_cast<int*>(smem_raw + cfg.o_flags)[tid] = 0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -899,7 +1091,8 @@ __global__ void __launch_bounds__(PipeTraits<NS>::kThreads, 1) nbctc_pipe_kernel
     if ((cfg.phase_mask & 5) && warp < cfg.NRW) row_warp_main<NS, LPR, CPL>(P, cfg, smem_raw, warp, lane);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PipeTraits<NS>::kChainRegs));
-    if (cfg.phase_mask & 2) chain_warp_main<NS, LPR>(P, cfg, lane);
+    if (cfg.phase_mask & 2)
+      chain_warp_main<NS, LPR>(P, cfg, lane, smem_u32(smem_raw + cfg.o_cring) + (warp - PipeTraits<NS>::kRowWarps) * CRing<NS>::BYTES);
   }
 }
 

@@ -168,10 +168,16 @@ int nbctc_match_frame_i32(const int32_t* pred, const int32_t* label, const float
                           int64_t C, int32_t* correct, nbctc_stream_t stream);
 
 /*
- * Host-buffer convenience entry points (every pointer is a HOST pointer): copy in,
- * run on `device`, copy the loss (and the gradient when grad_logits_host != NULL) back,
- * synchronise.  For non-PyTorch hosts and for end-to-end timing.
+ * Host-buffer plugin entry points (every pointer is a HOST pointer): what a caller without device memory of its own
+ * binds to.  The batch travels in chunks of sequences through three device slots -- chunk c+1 is copied in while
+ * chunk c runs and the gradient of chunk c-1 is copied back -- so the call runs at the speed of the PCIe link
+ * (pinned host memory: cudaHostAlloc / cudaHostRegister; pageable memory works but serialises the copies).
+ * The loss (and the gradient when grad_logits_host != NULL) is complete when the call returns.  loss_sum /
+ * loss_reduced are reduced on the host in float64 in ascending sequence order.  Device buffers and streams are kept
+ * per device between calls; nbctc_host_release(device) frees them.  Calls for one device are serialised.
  */
+int nbctc_host_release(int device);
+
 int nbctc_loss_grad_host_f32(int device, const float* logits_host, int64_t T, int64_t B, int64_t C,
                              const int32_t* labels_host, int64_t Lmax,
                              const int64_t* input_lengths_host, const int64_t* target_lengths_host,

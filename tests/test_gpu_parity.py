@@ -46,11 +46,11 @@ def assert_parity(loss, grad, ref, tol=TOL, scale=None):
     rg = rel_l2(grad, ref["grad"])
     assert rl < tol, f"loss rel err {rl}"
     assert rg < tol, f"grad L2 rel err {rg}"
-    # Linf relative to the largest gradient entry, reported bound 5e-5
+    # Linf relative to the largest gradient entry: the north-star 1e-5 as well
     # (floor: a tenth of the per-sequence weight, the natural size of a gradient entry -- the C=1 case has grad == 0)
     floor = 0.1 / grad.shape[1] if scale is None else scale
     linf = np.max(np.abs(grad - ref["grad"])) / max(np.max(np.abs(ref["grad"])), floor)
-    assert linf < 5 * tol, f"grad Linf rel err {linf}"
+    assert linf < tol, f"grad Linf rel err {linf}"
 
 
 @pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
@@ -469,7 +469,7 @@ def test_aligned16_flag_contract(nb):
     T, B, C, L = 64, 16, 157, 8
     full = int(lib.nbctc_workspace_bytes(T, B, C, L, 0, 0))
     lean = int(lib.nbctc_workspace_bytes(T, B, C, L, 0, _ffi.FLAG_ALIGNED16))
-    assert 0 < lean < full
+    assert 0 < lean <= full
     x, lab, il, tl = make_ctc_case(5, T, B, C, L)
     xs = torch.empty(x.size + 1, device=DEV)
     xd = xs[1:].view(T, B, C)          # 4-byte offset: not 16-byte aligned
