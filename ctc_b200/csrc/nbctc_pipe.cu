@@ -28,7 +28,7 @@ int g_env_tb = INT32_MIN, g_env_win = INT32_MIN, g_env_split = INT32_MIN, g_env_
 struct PipePlan {
   bool ok;
   PipeCfg cfg;
-  size_t o_ctr, o_hdr, o_grp, o_lab, o_doneA, o_doneB, o_doneC, o_aux, o_ab, ws_bytes;
+  size_t o_ctr, o_zeros, o_hdr, o_grp, o_lab, o_doneA, o_doneB, o_doneC, o_aux, o_ab, ws_bytes;
 };
 
 // prep kernel: one CTA per group
@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(128) pipe_prep_kernel(const Problem P, const P
     cfg.doneA[g] = 0; cfg.doneB[g] = 0; cfg.doneC[g] = 0;
     if (g == 0) { cfg.ctr[0] = 0; cfg.ctr[1] = 0; }
   }
+  if (g == 0 && tid < 64) cfg.zeros[tid] = 0.f;
+  {
+  }
 }
 
 PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
@@ -131,7 +134,10 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
     if (!placed) return pl;
   }
   // slabs per warp and task: 1 keeps the fewest groups in flight; long sequences take more (fewer label reloads)
-  const int ks = std::max(1, env_int_cached("NBCTC_PIPE_KS", T >= 2048 ? 4 : 1, &g_env_tb));
+  // (4 when every row warp of the machine gets at least 8 tasks of that size, else fewer)
+  const int64_t slabs_per_warp = ((B + c.GB - 1) / c.GB) * T / (148 * c.NRW);
+  const int ks_auto = slabs_per_warp >= 32 ? 4 : slabs_per_warp >= 16 ? 2 : 1;
+  const int ks = std::max(1, env_int_cached("NBCTC_PIPE_KS", ks_auto, &g_env_tb));
   c.TB = ks * c.NRW;
   c.TPG = (int)((T + c.TB - 1) / c.TB);
   c.NG = (int)((B + c.GB - 1) / c.GB);
@@ -151,7 +157,9 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   const bool split = env_int_cached("NBCTC_PIPE_SPLIT", 0, &g_env_split) != 0;
   // aux slots: everything stage A can be ahead of stage C, plus the groups the tickets in flight span
   const int span = c.grid / std::max(1, c.TPG) + 2;
-  c.NGS = split ? c.NG : std::min<int64_t>(c.NG, ((int64_t)c.wmax * c.grid + c.TPG - 1) / c.TPG + 2 * span + 4);
+  int64_t ngs = split ? c.NG : std::min<int64_t>(c.NG, ((int64_t)c.wmax * c.grid + c.TPG - 1) / c.TPG + 2 * span + 4);
+  c.NGS = 1;
+  while (c.NGS < ngs) c.NGS <<= 1;  // a power of two: slot = group & (NGS - 1)
   c.phase_mask = 7;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
@@ -166,6 +174,7 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   size_t w = 0;
   auto wtake = [&](size_t bytes) { size_t o = w; w = align_up(w + bytes, 256); return o; };
   pl.o_ctr = wtake(256);
+  pl.o_zeros = wtake(256);
   pl.o_hdr = wtake(sizeof(int4) * (size_t)B);
   pl.o_grp = wtake(sizeof(int2) * (size_t)c.NG);
   pl.o_lab = wtake(sizeof(int) * (size_t)B * c.Lpad);
@@ -210,6 +219,7 @@ int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream
   PipeCfg& c = pl.cfg;
   char* w = static_cast<char*>(ws) + pad;
   c.ctr = reinterpret_cast<int*>(w + pl.o_ctr);
+  c.zeros = reinterpret_cast<float*>(w + pl.o_zeros);
   c.hdr = reinterpret_cast<int4*>(w + pl.o_hdr);
   c.grp = reinterpret_cast<int2*>(w + pl.o_grp);
   c.lab = reinterpret_cast<int*>(w + pl.o_lab);

@@ -68,7 +68,8 @@ struct PipeCfg {
   int grid;
   uint32_t o_bar, o_meta, o_flags, o_ring, o_cring, smem_bytes;
   // workspace
-  int* ctr;      // [0] row ticket, [1] chain ticket
+  int* ctr;      // [0] (unused), [1] chain ticket
+  float* zeros;  // 256 bytes of zeros
   int4* hdr;     // [B] {T_b, L_b, largest duplicate rank, gradient weight bits}; T_b = 0 outside the parity domain
   int2* grp;     // [NG] {longest T_b of the group, sequences in the group}
   int* lab;      // [B][Lpad] class | duplicate rank << 22
@@ -268,6 +269,7 @@ struct ChainArgs {
   int want_grad;
   float* loss_out;
   uint32_t ring;    // shared-memory ring of this warp (byte address in the shared window)
+  const float* zeros;  // >= 64 bytes of zeros (emissions of chain lanes that hold no state)
 };
 
 // Stored chain states: a non-negative double as 32 bits = 11-bit exponent + 21-bit mantissa (round to nearest).
@@ -323,14 +325,14 @@ struct ChainRun {
   double x[NS], sum[NS];
   int e;
   double fac;
-  int64_t pstep, abstep;
+  int64_t pstep, gstep, abstep;
   const float* pld;
   const uint32_t* old_;
   float* gst;
   uint32_t* abw;
   uint32_t slot_addr, ring_lo, ring_hi;  // ring position of the step that is consumed / refilled next
-  int Ez;
-  double zinv;
+  int Ez, kx;
+  double zinv, sA, sB;
 
   __device__ __forceinline__ ChainRun(const ChainArgs& a_, int lane_) : a(a_), lane(lane_), hl(lane_ & 15), isb(lane_ >= 16) {}
 
@@ -344,7 +346,8 @@ struct ChainRun {
       cp_async<8>(dst + lane * RG::PB, pld);
     } else {
 #pragma unroll
-      for (int i = 0; i < NS; i += 4) cp_async<16>(dst + lane * RG::PB + i * 4, pld + i);
+      for (int i = 0; i < NS; i += 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + lane * RG::PB + i * 4), "l"(pld + i) : "memory");
     }
     pld += pstep;
   }
@@ -365,7 +368,7 @@ struct ChainRun {
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(raw[i]), "=f"(raw[i + 1]), "=f"(raw[i + 2]), "=f"(raw[i + 3]) : "r"(src + i * 4));
     }
 #pragma unroll
-    for (int j = 0; j < NS; ++j) p[j] = live ? (double)(isb ? raw[NS - 1 - j] : raw[j]) : 0.0;
+    for (int j = 0; j < NS; ++j) p[j] = (double)(isb ? raw[NS - 1 - j] : raw[j]);  // (lanes without a state fetch zeros)
   }
   // stored states of the other direction (its lane 15-hl holds this lane's states in reversed order) and its scale
   __device__ __forceinline__ void read_o(double (&o)[NS], int& eo) const {
@@ -375,7 +378,7 @@ struct ChainRun {
     for (int i = 0; i < NSP; i += 4)
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i]), "=r"(v[i + 1]), "=r"(v[i + 2]), "=r"(v[i + 3]) : "r"(src + i * 4));
 #pragma unroll
-    for (int q = 0; q < NS; ++q) o[q] = live ? unpack_state(v[NS - 1 - q]) : 0.0;
+    for (int q = 0; q < NS; ++q) o[q] = unpack_state(v[NS - 1 - q]);
     eo = (int)v[NS];
   }
   __device__ __forceinline__ void store_state(bool ok) {
@@ -450,9 +453,13 @@ struct ChainRun {
       fetch_o(slot_addr);
       cp_async_commit();
       advance_slot();
-      // gamma = sum * stored * 2^(e + eo - Ez) / zhat; the power of two is split over both factors (range)
-      const int dd = e + eo - Ez;
-      const double sA = pow2z(dd >> 1), sB = pow2z(dd - (dd >> 1)) * zinv;
+      // gamma = sum * stored * 2^(e + eo - Ez) / zhat; the power of two is split over both factors (range).  e changes
+      // at this direction's block entries (j = 0), eo when the other direction's block changes (j = kx)
+      if (j == 0 || j == kx) {
+        const int dd = e + eo - Ez;
+        sA = pow2z(dd >> 1);
+        sB = pow2z(dd - (dd >> 1)) * zinv;
+      }
       chain_step<NS, true>(x, sum, p, fac);
       float g[NS], gm[NS];
 #pragma unroll
@@ -461,7 +468,7 @@ struct ChainRun {
       for (int q = 0; q < NS; ++q) gm[q] = isb ? g[NS - 1 - q] : g[q];
       // (alpha's last iteration is beyond T_b when T_b is odd)
       stcg_vec<NS>(gst, live && (!kTail || k < Ha) && (isb || k < Ha - odd), gm);
-      gst += pstep;
+      gst += gstep;
     }
   }
 
@@ -482,7 +489,9 @@ struct ChainRun {
     for (int j = 0; j < NS; ++j) x[j] = ((smask >> j) & 1u) ? 1.0 : 0.0;
     e = 0;
     fac = hl == 0 ? 0.0 : 1.0;
-    pstep = isb ? -a.pstride : a.pstride;  // alpha walks up in time, beta walks down (both halves)
+    // alpha walks up in time, beta walks down (both halves); lanes without a state read a block of zeros
+    pstep = !live ? 0 : isb ? -a.pstride : a.pstride;
+    gstep = isb ? -a.pstride : a.pstride;
     abstep = isb ? -(int64_t)ABS : (int64_t)ABS;
     ring_lo = a.ring;
     ring_hi = a.ring + RG::BYTES;
@@ -490,7 +499,7 @@ struct ChainRun {
 
     // ---- first half (beta's iteration 0 is virtual when T_b is odd: its row T_b is padding or unused)
     const int t1_0 = isb ? Tb - 1 + odd : 0;
-    pld = a.paux + soff + (int64_t)t1_0 * a.pstride;
+    pld = live ? a.paux + soff + (int64_t)t1_0 * a.pstride : a.zeros;
     for (int j = 0; j < U; ++j) {
       fetch_p(ring_lo + j * RG::STEP);
       cp_async_commit();
@@ -512,8 +521,8 @@ struct ChainRun {
     // ---- second half
     const int t2_0 = isb ? Ha - 1 : Ha;
     old_ = a.ab + (int64_t)t2_0 * ABS + (15 - hl) * NSP;
-    pld = a.paux + soff + (int64_t)t2_0 * a.pstride;
-    gst = const_cast<float*>(pld);  // gamma' overwrites the emissions of the same time step
+    gst = a.paux + soff + (int64_t)t2_0 * a.pstride;  // gamma' overwrites the emissions of the same time step
+    pld = live ? gst : a.zeros;
     slot_addr = ring_lo;
     for (int j = 0; j < U; ++j) {
       fetch_p(ring_lo + j * RG::STEP);
@@ -532,7 +541,7 @@ struct ChainRun {
       int eo0;
       cp_async_wait<U - 1>();
       read_o(o, eo0);
-      const int ms = top_exponent<NS>(sum), mo = top_exponent<NS>(o);
+      const int ms = live ? top_exponent<NS>(sum) : kSent, mo = top_exponent<NS>(o);
       double part = 0.0;
       int ep = kSent;
       if (ms != kSent && mo != kSent) {
@@ -564,6 +573,7 @@ struct ChainRun {
       }
     }
     if (a.want_grad) {
+      kx = Ha & 7;  // the other direction's block of 8 steps changes when Ha-1-k crosses a multiple of 8
       int base = 0;
       for (; base + UB <= Ha; base += UB) body2<false>(base);
       if (base < Ha) body2<true>(base);
@@ -774,11 +784,11 @@ struct PRows {
       }
       // states L_b .. roundup(L_b, NS)-1 share a chain lane with real states: their emission is 0
       const int Lz = (Lb + NS - 1) / NS * NS;
+      float* ar = arow + li;
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
-        const int st = li + j * LPR;
-        if (labr[j] >= 0) __stcg(arow + st, fmaxf(ex2f(fmaf(xv[j], kLog2e, -mb)) * rs, kPMin));
-        else if (st >= Lb && st < Lz) __stcg(arow + st, 0.f);
+        const float pv = labr[j] >= 0 ? fmaxf(ex2f(fmaf(xv[j], kLog2e, -mb)) * rs, kPMin) : 0.f;
+        if (li + j * LPR < Lz) __stcg(ar + j * LPR, pv);
       }
     }
   }
@@ -864,13 +874,26 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
   const uint32_t aux_row_bytes = (uint32_t)cfg.AUXF * 4u;
 
   // producer cursor (warp-uniform)
-  int cur_type = 0, cur_gi = 0, cur_t = 0, cur_tend = 0, cur_first = 0, cur_cnt = 0;
+  int cur_type = 0, cur_gi = 0, cur_t = 0, cur_tend = 0, cur_first = 0;
+  // positions ka (stage A) and kc (stage C) of the CTA's task sequence c0, c0 + G, ... as (group, time block)
+  const int Gq = G / cfg.TPG, Gr = G - Gq * cfg.TPG;
   int ka = 0, kc = 0;
+  int a_gi = c0 / cfg.TPG, a_tb = c0 - a_gi * cfg.TPG;
+  int c_gi = a_gi, c_tb = a_tb;
+  auto advance = [&](int& gi, int& tb) {
+    tb += Gr;
+    gi += Gq;
+    if (tb >= cfg.TPG) {
+      tb -= cfg.TPG;
+      ++gi;
+    }
+  };
   bool finished = false;
-  int head = 0, tail = 0, inflight = 0, attempts = 0;
+  int head = 0, tail = 0, inflight = 0, attempts = 0, task_n = 0;
   uint32_t par = 0;
+  const size_t aux_slot_rows = (size_t)T + 2 * kPadRows;
 
-  auto aux_row = [&](int gi, int t) { return cfg.aux + ((size_t)(gi % cfg.NGS) * (T + 2 * kPadRows) + kPadRows + t) * cfg.AUXF; };
+  auto aux_row = [&](int gi, int t) { return cfg.aux + ((size_t)(gi & (cfg.NGS - 1)) * aux_slot_rows + kPadRows + t) * cfg.AUXF; };
   // Dependency `which` (0: the chains of a stage-C task's group, 1: the aux slot of a stage-A task) of position k.
   // All row warps of the CTA wait for the same things in the same order: what one of them has seen is cached in shared
   // memory, and only warp k % NRW polls the global counter at full rate.
@@ -879,7 +902,8 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
       __threadfence_block();
       return true;
     }
-    if ((k % NRW) != rw && ((++attempts) & 7) != 0) return false;
+    const int poller = (k & 15) < NRW ? (k & 15) : 0;
+    if (poller != rw && ((++attempts) & 7) != 0) return false;
     int ok = 0;
     if (lane == 0) ok = ld_acquire(ctr) >= want;
     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -892,13 +916,17 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
   auto prefetch_labels = [&](int gi, unsigned char* slot) {
     const int64_t b0 = (int64_t)gi * GB;
     const int gcnt = (int)min((int64_t)GB, P.B - b0);
-    unsigned char* lb = slot + cfg.RSg + aux_row_bytes;
+    const uint32_t lb = smem_u32(slot) + cfg.RSg + aux_row_bytes;
     const int nlab = gcnt * (Lpad / 4);
     const char* src = reinterpret_cast<const char*>(cfg.lab + b0 * Lpad);
-    for (int c = lane; c < nlab; c += 32)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + c * 16)), "l"(src + (size_t)c * 16) : "memory");
+    if constexpr (GB * (Lpad / 4) <= 32) {
+      if (lane < nlab) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + lane * 16), "l"(src + lane * 16) : "memory");
+    } else {
+      for (int c = lane; c < nlab; c += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + c * 16), "l"(src + (size_t)c * 16) : "memory");
+    }
     if (lane < gcnt)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + GB * Lpad * 4 + lane * 16)),
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + GB * Lpad * 4 + lane * 16),
                    "l"(reinterpret_cast<const char*>(cfg.hdr + b0) + lane * 16)
                    : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -908,37 +936,42 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
   auto try_produce = [&]() -> int {
     for (;;) {
       if (cur_type == 0) {
-        const int64_t na = (int64_t)c0 + (int64_t)ka * G, nc = (int64_t)c0 + (int64_t)kc * G;
-        const bool haveA = do_a && na < NA, haveC = do_c && nc < NA;
+        const bool haveA = do_a && a_gi < cfg.NG, haveC = do_c && c_gi < cfg.NG;
         if (!haveA && !haveC) {
           finished = true;
           return 0;
         }
         bool started = false;
         if (haveC && (kc < ka || !haveA)) {
-          const int gi = (int)nc / cfg.TPG, tb = (int)nc - gi * cfg.TPG;
+          const int gi = c_gi;
           const int2 gg = __ldg(&cfg.grp[gi]);
           if (dep_ready(0, kc, cfg.doneB + gi, gg.y)) {  // the group's chains
-            fence_proxy_async_all();  // gamma' and row statistics were written through the generic proxy
+            // gamma' and the row statistics were written through the generic proxy, the bulk copies read them
+            // through the async proxy
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             const int Tg = gg.x;
-            const int t0 = tb * cfg.TB + rw, t1 = min(T, (tb + 1) * cfg.TB), tl = min(t1, Tg);
+            const int t0 = c_tb * cfg.TB + rw, t1 = min(T, (c_tb + 1) * cfg.TB), tl = min(t1, Tg);
             prod.set_group(gi);
             // rows beyond the group's longest input: zeros, written directly (ragged batches only)
-            for (int t = t0 + ((max(Tg - t0, 0) + NRW - 1) / NRW) * NRW; t < t1; t += NRW) {
-              float* dst = P.grad + ((int64_t)t * P.B + prod.b0) * P.C;
-              const int n = prod.gcnt * (int)P.C;
-              for (int c = lane; c < n; c += 32) dst[c] = 0.f;
+            if (t1 > Tg) {
+              int t = t0;
+              while (t < Tg) t += NRW;
+              for (; t < t1; t += NRW) {
+                float* dst = P.grad + ((int64_t)t * P.B + prod.b0) * P.C;
+                const int n = prod.gcnt * (int)P.C;
+                for (int c = lane; c < n; c += 32) dst[c] = 0.f;
+              }
             }
             if (t0 < tl) {
               cur_type = kMetaC; cur_gi = gi; cur_t = t0; cur_tend = tl; cur_first = 1;
-              cur_cnt = (tl - t0 + NRW - 1) / NRW;
             }
             ++kc;
+            advance(c_gi, c_tb);
             started = true;
           }
         }
         if (!started && haveA && (!do_c || ka - kc < cfg.wmax)) {
-          const int gi = (int)na / cfg.TPG, tb = (int)na - gi * cfg.TPG;
+          const int gi = a_gi;
           bool ok = true;
           if (gi >= cfg.NGS) {
             // the aux slot of this group was used by group gi - NGS: its last reader must be done
@@ -948,13 +981,13 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
           }
           if (ok) {
             const int Tg = __ldg(&cfg.grp[gi].x);
-            const int t0 = tb * cfg.TB + rw, t1 = min(min(T, (tb + 1) * cfg.TB), Tg);
+            const int t0 = a_tb * cfg.TB + rw, t1 = min(min(T, (a_tb + 1) * cfg.TB), Tg);
             if (t0 < t1) {
               cur_type = kMetaA; cur_gi = gi; cur_t = t0; cur_tend = t1; cur_first = 1;
-              cur_cnt = (t1 - t0 + NRW - 1) / NRW;
               prod.set_group(gi);
             }
             ++ka;
+            advance(a_gi, a_tb);
             started = true;
           }
         }
@@ -968,7 +1001,7 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
       unsigned char* slot = ring + (size_t)head * cfg.SLOTB;
       if (cur_first) prefetch_labels(cur_gi, slot);
       if (lane == 0) {
-        meta[head] = make_int4(cur_type | (cur_first ? kMetaFirst : 0) | (last ? kMetaLast : 0), t, cur_gi, cur_cnt);
+        meta[head] = make_int4(cur_type | (cur_first ? kMetaFirst : 0) | (last ? kMetaLast : 0), t, cur_gi, 0);
         if (cur_type == kMetaA) prod.issue_load(slot, &bars[head], t, pol_keep, nullptr, 0);
         else prod.issue_load(slot, &bars[head], t, pol_stream, aux_row(cur_gi, t), aux_row_bytes);
       }
@@ -981,12 +1014,22 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
     }
   };
 
+  int* sig_ctr = nullptr;
+  int sig_n = 0;
+  auto flush_signal = [&]() {
+    if (sig_ctr != nullptr) {
+      __syncwarp();  // every lane's emission stores are ordered before lane 0's release
+      if (lane == 0) red_release_add(sig_ctr, sig_n);
+      sig_ctr = nullptr;
+    }
+  };
   unsigned long long t_idle = 0;
   for (;;) {
     while (inflight < D - 1) {
       if (!try_produce()) break;
     }
     if (inflight == 0) {
+      flush_signal();
       if (finished) break;
       const unsigned long long now = gtime();
       if (t_idle == 0) t_idle = now;
@@ -998,6 +1041,7 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
     // ---- consume slot `tail`
     mbar_wait(&bars[tail], (par >> tail) & 1u);
     par ^= 1u << tail;
+    flush_signal();
     const int4 mt = meta[tail];
     unsigned char* slot = ring + (size_t)tail * cfg.SLOTB;
     const int type = mt.x & 3, t = mt.y, gi = mt.z;
@@ -1005,24 +1049,26 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();
       cons.begin_task(gi, slot + cfg.RSg + aux_row_bytes);
+      task_n = 0;
     }
+    ++task_n;
     if (type == kMetaA) {
       cons.stage_a(t, slot, aux_row(gi, t));
       if (lane == 0) bulk_commit();  // one (empty) group per consumed slot keeps the wait below uniform
       if (mt.x & kMetaLast) {
-        fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0) red_release_add(cfg.doneA + gi, mt.w);
+        // the release of this task is issued when the next slab has landed (or the warp runs dry): the emission stores
+        // have reached L2 by then and the fence does not wait for them
+        sig_ctr = cfg.doneA + gi;
+        sig_n = task_n;
       }
     } else {
       cons.stage_c(t, slot, reinterpret_cast<const float*>(slot + cfg.RSg));
       fence_proxy_async();  // the slab is read by the async proxy (bulk store)
       __syncwarp();
       if (lane == 0) cons.issue_store(slot, t, pol_stream);
-      if (mt.x & kMetaLast) {
-        __syncwarp();
-        if (lane == 0) red_release_add(cfg.doneC + gi, mt.w);
-      }
+      // (relaxed: the aux rows of this task have been read -- they sit in shared memory -- and nothing was written
+      // that another thread reads)
+      if ((mt.x & kMetaLast) && lane == 0) atomicAdd(cfg.doneC + gi, task_n);
     }
     tail = tail + 1 == D ? 0 : tail + 1;
     --inflight;
@@ -1064,6 +1110,7 @@ __device__ __forceinline__ void chain_warp_main(const Problem& P, const PipeCfg&
       a.pstride = cfg.AUXF;
       a.ab = cfg.ab + ((slot * GB + sq) * TP + kPadRows) * (size_t)(16 * CRing<NS>::NSP);
       a.ring = ring;
+      a.zeros = cfg.zeros;
       a.Tb = h.x; a.Lb = h.y; a.wgt = __int_as_float(h.w);
       a.want_grad = cfg.want_grad;
       a.loss_out = P.loss + b;
