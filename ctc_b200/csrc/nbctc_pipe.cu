@@ -23,7 +23,7 @@ int env_int_cached(const char* name, int dflt, int* cache) {
   return *cache;
 }
 int g_env_tb = INT32_MIN, g_env_win = INT32_MIN, g_env_split = INT32_MIN, g_env_d = INT32_MIN, g_env_nrw = INT32_MIN,
-    g_env_lpr = INT32_MIN;
+    g_env_lpr = INT32_MIN, g_env_keep = INT32_MIN;
 
 struct PipePlan {
   bool ok;
@@ -161,6 +161,7 @@ PipePlan make_pipe_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   c.NGS = 1;
   while (c.NGS < ngs) c.NGS <<= 1;  // a power of two: slot = group & (NGS - 1)
   c.phase_mask = 7;
+  c.keep_logits = env_int_cached("NBCTC_PIPE_KEEP", 2, &g_env_keep);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (uint32_t)o; };
   c.o_bar = take(sizeof(uint64_t) * c.NRW * c.D);

@@ -65,6 +65,7 @@ struct PipeCfg {
   int wmax;     // stage A runs at most `wmax` positions of a CTA's ticket sequence ahead of stage C
   int phase_mask;  // bit 0 stage A, bit 1 stage B, bit 2 stage C (all set in the fused launch)
   int want_grad;
+  int keep_logits;  // L2 policy of the stage-A logits read: 0 evict_first, 1 normal, 2 evict_last
   int grid;
   uint32_t o_bar, o_meta, o_flags, o_ring, o_cring, smem_bytes;
   // workspace
@@ -870,7 +871,13 @@ __device__ __forceinline__ void row_warp_main(const Problem& P, const PipeCfg& c
   const int NA = cfg.NG * cfg.TPG;
   const int T = (int)P.T;
   const int G = (int)gridDim.x, c0 = (int)blockIdx.x;
-  const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  // L2 policy of the stage-A read of the logits: evict_last keeps them for stage C when the window of groups between
+  // the stages fits into L2 (cfg.keep_logits), otherwise they are streamed like everything else
+  uint64_t pol_keep;
+  if (cfg.keep_logits == 2) pol_keep = policy_evict_last();
+  else if (cfg.keep_logits == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+  else pol_keep = policy_evict_first();
+  const uint64_t pol_stream = policy_evict_first();
   const uint32_t aux_row_bytes = (uint32_t)cfg.AUXF * 4u;
 
   // producer cursor (warp-uniform)
