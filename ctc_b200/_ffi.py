@@ -16,6 +16,7 @@ FLAG_GENERIC = 1
 FLAG_NO_GRAD = 2
 FLAG_ALIGNED16 = 4
 FLAG_LOCKSTEP = 8
+FLAG_PIPELINE = 16
 
 _lib = None
 

@@ -2,6 +2,7 @@
 // selection (fused sm_100a kernel vs generic three-kernel path), backward-time rescale,
 // and the host-buffer convenience entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -45,6 +46,18 @@ __global__ void scale_grad_kernel(float* __restrict__ g, int64_t n_vec4, int64_t
   }
 }
 
+// which fused single-label kernel: NBCTC_FLAG_PIPELINE / NBCTC_FLAG_LOCKSTEP, else the NBCTC_PATH environment variable
+// ("pipe" | "lockstep", read once), else the lock-step kernel
+bool want_pipeline(uint32_t flags) {
+  if (flags & NBCTC_FLAG_PIPELINE) return true;
+  if (flags & NBCTC_FLAG_LOCKSTEP) return false;
+  static const int env = [] {
+    const char* v = getenv("NBCTC_PATH");
+    return (v && v[0] == 'p') ? 1 : 0;
+  }();
+  return env != 0;
+}
+
 int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void* tg, int64_t Lmax,
                  const void* il, const void* tl, const void* loss) {
   if (T < 1 || B < 1 || C < 1 || Lmax < 1) {
@@ -71,7 +84,7 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
     return NBCTC_ERR_INVALID_ARG;
   }
   const bool use_fused = shape_ok && fused_pointers_ok(p);
-  const bool use_pipe = !binary && !(flags & (NBCTC_FLAG_GENERIC | NBCTC_FLAG_LOCKSTEP)) && fused_pointers_ok(p) &&
+  const bool use_pipe = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_pipeline(flags) && fused_pointers_ok(p) &&
                         pipe_supported(p.T, p.B, p.C, p.Lmax);
   if (use_pipe) {
     rc = pipe_launch(p, ws, ws_bytes, stream);
@@ -260,7 +273,7 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   // the generic size is kept as a floor: a call with 16-byte misaligned tensors falls back to that path
   size_t f = 0;
   if (fused_supported(T, B, C, Lmax, binary != 0)) f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
-  if (!binary && !(flags & NBCTC_FLAG_LOCKSTEP) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
+  if (!binary && want_pipeline(flags) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
   if (f) return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
   if (binary && tiled_bin_supported(T, B, C, Lmax)) return align_up(g, 256) + tiled_bin_workspace_bytes(T, B, C, Lmax);
   return g;

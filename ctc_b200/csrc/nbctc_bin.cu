@@ -40,7 +40,7 @@ struct TiledWs {
   int* flag;            // != 0: the targets are outside this path's domain -> generic kernels
   uint32_t* cmask;      // [B][C][LW]    states that contain the class
   double* ckpt;         // [B][NT][Lpad] alpha checkpoints
-  int* cke;             // [B][NT]       their exponents
+  int* cke;             // [B][NT][16]   their lane scales
   float* emis;          // (T,B,Lmax)    emissions p_t(s), overwritten by gamma
   int LW, NT, Lpad;
 };
@@ -59,7 +59,7 @@ Layout layout(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   l.o_cmask = take(sizeof(uint32_t) * (size_t)B * C * l.LW);
   l.o_ckpt = take(sizeof(double) * (size_t)B * l.NT * l.Lpad);
-  l.o_cke = take(sizeof(int) * (size_t)B * l.NT);
+  l.o_cke = take(sizeof(int) * (size_t)B * l.NT * 16);
   l.o_emis = take(sizeof(float) * (size_t)T * B * Lmax);
   l.total = off;
   return l;
@@ -227,57 +227,58 @@ __device__ __forceinline__ void lat_phase1_regs(double (&x)[NS], stream::ChainSc
   const int hl = lane & (W - 1);
   double sum[NS];
   if (k > 0) {
-    c.Ea += rescale_group<NS, W>(x);
+    lane_rescale<NS, W, LaneDec<NS, TT>::value>(x, c.e, c.fac, hl);
     if (lane < W) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) ck[(k * NS + j) * W] = x[j];
-      if (lane == 0) cke[k] = c.Ea;
+      cke[k * W + lane] = c.e;
     }
   }
 #pragma unroll
   for (int i = 0; i < TT; ++i) {
-    if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry);
-    else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0);
+    if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry, c.fac);
+    else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0, c.fac);
   }
   c.carry = 0.0;
 }
 // pr[jj]: the lane's emissions of its jj-th step (alpha walks up the tile, beta down), in the lane's state order
 template <int NS, int W, int TT, int AS>
-__device__ __forceinline__ void lat_phase2_regs(double (&x)[NS], stream::ChainScal& c, int lane, bool isb, int Eb_all,
-                                                const double (&ckv)[NS], int EaK, int k, const double (&pr)[TT][NS],
-                                                double* __restrict__ abt, double* s2_out) {
+__device__ __forceinline__ void lat_phase2_regs(double (&x)[NS], stream::ChainScal& c, int lane, bool isb, const double (&ckv)[NS],
+                                                int eck, int k, const double (&pr)[TT][NS], double* __restrict__ abt) {
   using namespace stream;
   constexpr int Lpad = W * NS;
   const int hl = lane & (W - 1);
   double sum[NS];
-  const int d = EaK + Eb_all - c.Ez;
-  const double s1 = pow2i(d / 2);
-  const double s2 = -(pow2i(d - d / 2) * c.zinv);
-  if (lane == 0 && !isb) *s2_out = s2;
   if (!isb) {
-    if (k == 0) {
+    c.e = k == 0 ? 0 : eck;
+    c.carry = (k == 0 && hl == 0) ? 1.0 : 0.0;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) x[j] = 0.0;
-      c.carry = (lane == 0) ? s1 : 0.0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) x[j] = ckv[j] * s1;
-    }
+    for (int j = 0; j < NS; ++j) x[j] = k == 0 ? 0.0 : ckv[j];
   }
+  {
+    const int eu = __shfl_up_sync(0xffffffffu, c.e, 1, W);
+    if (!isb) c.fac = hl == 0 ? 0.0 : pow2z(eu - c.e);
+  }
+  const double bs = isb ? pow2z(c.e + (k == 0 ? 0 : eck) - c.Ez) * c.zinv : 1.0;
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
   const int sdir = isb ? -1 : 1;
   double* dst = abt + (isb ? TT * AS : 0) + s0;
 #pragma unroll
   for (int jj = 0; jj < TT; ++jj) {
     const int i = isb ? (TT - 1 - jj) : jj;
-    if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry);
-    else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0);
+    if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry, c.fac);
+    else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0, c.fac);
 #pragma unroll
-    for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
+    for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
   }
   c.carry = 0.0;
-  const int e = rescale_group<NS, W>(x);
-  if (isb) c.Eb += e;
+  int e2 = c.e;
+  double f2 = c.fac;
+  lane_rescale<NS, W, LaneDec<NS, TT>::value>(x, e2, f2, hl);
+  if (isb) {
+    c.e = e2;
+    c.fac = f2;
+  }
 }
 
 // The emission tile holds p_t(s) = exp(e_t(s) - rowc_t) (K1; zeros for states >= L_b).  NS = 2 and an even Lmax: full
@@ -289,14 +290,13 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   if (*w.flag != 0) return;
   using namespace stream;
   constexpr int W = 16, TT = 8, Lpad = 16 * NS, PS = Lpad + 8, AS = Lpad + 8;
-  constexpr int kWarpBytes = TT * PS * 4 + 2 * TT * AS * 8 + 16;
+  constexpr int kWarpBytes = TT * PS * 4 + 2 * TT * AS * 8;
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * kLatWarps + warp;
   if (b >= p.B) return;
   float* pt = reinterpret_cast<float*>(smraw + (size_t)warp * kWarpBytes);
   double* abt = reinterpret_cast<double*>(pt + TT * PS);
-  double* s2p = abt + 2 * TT * AS;
   const int64_t Tb64 = p.in_len[b], Lb64 = p.tgt_len[b];
   if (!seq_feasible(Tb64, Lb64, p.T, p.Lmax)) {
     if (lane == 0) p.loss[b] = INFINITY;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   const int Tb = (int)Tb64, Lb = (int)Lb64, Lmax = (int)p.Lmax;
   const int NTb = (Tb + TT - 1) / TT;
   double* ck = w.ckpt + ((size_t)b * w.NT) * Lpad + (lane & (W - 1));
-  int* cke = w.cke + (size_t)b * w.NT;
+  int* cke = w.cke + (size_t)b * w.NT * W;  // [NT][W] lane scales of the checkpoints
   const bool isb = lane >= 16;
 
   constexpr int NPR = Lpad / 32;  // floats per lane and tile row
@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   for (int j = 0; j < NS; ++j) cx[j] = 0.0;
   chain.carry = (lane == 0) ? 1.0 : 0.0;
   chain.zinv = 0.0;
-  chain.Ea = 0; chain.Eb = 0; chain.Ez = 0;
+  chain.e = 0; chain.Ez = 0;
+  chain.fac = (lane & (W - 1)) == 0 ? 0.0 : 1.0;
   // ---- phase 1: alpha, one checkpoint per tile
   if (NTf > 0) fetch2(0, false);
   for (int k = 0; k < NTb; ++k) {
@@ -380,34 +381,33 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
   if (NTf > 0) fetch2(NTf - 1, true);
   for (int k = NTb - 1; k >= 0; --k) {
     double ckv[NS];
-    int EaK = 0;
+    int eck = 0;
     if (k > 0) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) ckv[j] = ck[(k * NS + j) * W];
-      EaK = cke[k];
+      // the alpha direction's own lane scale; the beta direction takes the scale of the alpha lane with the same states
+      eck = cke[k * W + (isb ? W - 1 - (lane & (W - 1)) : (lane & (W - 1)))];
     } else {
 #pragma unroll
       for (int j = 0; j < NS; ++j) ckv[j] = 0.0;
     }
-    const int Eb_all = __shfl_sync(0xffffffffu, chain.Eb, 16);
     bool done = false;
     if constexpr (NS == 2) {
       if (k < NTf) {
         double pr[TT][2];
         widen(pr, true);
         if (k > 0) fetch2(k - 1, true);
-        lat_phase2_regs<2, W, TT, AS>(cx, chain, lane, isb, Eb_all, ckv, EaK, k, pr, abt, s2p);
+        lat_phase2_regs<2, W, TT, AS>(cx, chain, lane, isb, ckv, eck, k, pr, abt);
         done = true;
       }
     }
     if (!done) {
       stage(k);
       __syncwarp();
-      chain_phase2<NS, W, TT, PS, AS>(cx, chain, lane, isb, Eb_all, Tb, ckv, EaK, k, pt, abt, s2p);
+      chain_phase2<NS, W, TT, PS, AS>(cx, chain, lane, isb, Tb, ckv, eck, k, pt, abt);
     }
     __syncwarp();
-    // gamma_t(s) = alpha_t(s) beta_t(s) / Z (s2 = -1/Z and the tile exponents) -> emission tile
-    const double s2 = *s2p;
+    // gamma_t(s) = alpha entry * beta entry (chain_phase2 folds 1/Z and the lane scales into the beta tile) -> emission tile
     const int t0 = k * TT, nv = min(TT, Tb - t0);
     float* pe = e_b + (int64_t)t0 * estride;
 #pragma unroll
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kLatWarps * 32, NS == 2 ? 7 : 1) lattice_tile_
 #pragma unroll
       for (int q = 0; q < NPR; ++q) {
         const int st = lane + 32 * q;
-        if (r < nv && sv[q]) pe[32 * q] = -(float)(abt[r * AS + st] * (abt[(TT + r) * AS + st] * s2));
+        if (r < nv && sv[q]) pe[32 * q] = (float)(abt[r * AS + st] * abt[(TT + r) * AS + st]);
       }
       pe += estride;
     }
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kGradWarps * 32, 2) bin_grad_kernel(Problem p,
 template <int NS>
 int launch_lattice(const Problem& p, const TiledWs& w, cudaStream_t stream) {
   constexpr int Lpad = 16 * NS, PS = Lpad + 8, AS = Lpad + 8;
-  constexpr int kWarpBytes = 8 * PS * 4 + 2 * 8 * AS * 8 + 16;
+  constexpr int kWarpBytes = 8 * PS * 4 + 2 * 8 * AS * 8;
   const size_t smem = (size_t)kLatWarps * kWarpBytes;
   auto kern = lattice_tile_kernel<NS>;
   if (smem > 48 * 1024) NBCTC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

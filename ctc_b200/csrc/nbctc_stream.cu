@@ -83,7 +83,7 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
     c.o_info = take(sizeof(int) * 4 * kMaxGB);
     c.o_lab = take(sizeof(int) * gb * c.Lpad);
     c.o_ckpt = take(ck_glob ? 16 : sizeof(double) * (size_t)gb * c.NTmax * c.Lpad);
-    c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax);
+    c.o_cke = take(ck_glob ? 16 : sizeof(int) * (size_t)gb * c.NTmax * (c.NS > 2 ? 32 : 16));
     c.o_ptile = take(sizeof(float) * 2 * (size_t)gb * PSEQ);
     c.o_s2 = take(sizeof(double) * 2 * gb);
     c.o_pub = take(16 * (size_t)gb);
@@ -107,7 +107,7 @@ size_t plan_ws_bytes(const Plan& pl, int64_t T, int64_t B) {
   if (!pl.ok) return off;
   (void)T;
   off = align_up(off + sizeof(double) * (size_t)B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
-  off = align_up(off + sizeof(int) * (size_t)B * pl.cfg.NTmax, 256);
+  off = align_up(off + sizeof(int) * (size_t)B * pl.cfg.NTmax * (pl.cfg.NS > 2 ? 32 : 16), 256);
   return off;
 }
 

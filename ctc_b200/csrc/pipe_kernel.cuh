@@ -92,15 +92,9 @@ namespace pipe {
 
 using namespace stream;
 
-constexpr int kSent = -(1 << 28);  // "no exponent": an all-zero lane
 constexpr int kRB = 8;             // chain steps between two rescales
 constexpr int kPadRows = 16;       // padding rows before and after every aux / stored-state tile (chain prefetch)
 
-// exact 2^e; 0 below the normal range, 2^1023 above
-__device__ __forceinline__ double pow2z(int e) {
-  if (e < -1022) return 0.0;
-  return __hiloint2double((1023 + min(e, 1023)) << 20, 0);
-}
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -228,36 +222,10 @@ __device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], c
   x[0] = fma(up, p0f, t[0]);
 }
 
-// exponent field - 1023 of the largest of NS non-negative values; kSent if that is zero / denormal / not finite
-template <int NS>
-__device__ __forceinline__ int top_exponent(const double (&v)[NS]) {
-  int hi = __double2hiint(v[0]);
-#pragma unroll
-  for (int j = 1; j < NS; ++j) hi = max(hi, __double2hiint(v[j]));
-  const int ef = hi >> 20;
-  return (ef > 0 && ef < 0x7ff) ? ef - 1023 : kSent;
-}
-
-// Rescale at the start of a block of 8 steps.  Lane scale e_l = max_{k<=l}(A_k - DEC (l-k)), A_k = absolute
-// exponent of lane k's largest state: every lane is scaled to its own magnitude unless mass from a much larger
-// lane upstream is about to arrive (mass only moves to higher positions).  Values that fall 2^-1022 below the lane
-// scale flush to zero; they are below float64 resolution of what that mass turns them into.
+// rescale at the start of a block of 8 steps (stream_kernel.cuh: lane_rescale)
 template <int NS>
 __device__ __forceinline__ void block_entry(double (&x)[NS], int& e, double& fac, int hl) {
-  const int te = top_exponent<NS>(x);
-  int env = te == kSent ? kSent : e + te;
-#pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {
-    const int sh = __shfl_up_sync(0xffffffffu, env, o, 16);
-    if (hl >= o && sh > kSent / 2) env = max(env, sh - CG<NS>::DEC * o);
-  }
-  const int en = env > kSent / 2 ? env : e;
-  const double sc = pow2z(e - en);
-#pragma unroll
-  for (int j = 0; j < NS; ++j) x[j] *= sc;
-  e = en;
-  const int eu = __shfl_up_sync(0xffffffffu, en, 1, 16);
-  fac = hl == 0 ? 0.0 : pow2z(eu - en);
+  lane_rescale<NS, 16, CG<NS>::DEC>(x, e, fac, hl);
 }
 
 struct ChainArgs {

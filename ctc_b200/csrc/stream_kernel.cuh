@@ -48,7 +48,7 @@ struct StreamCfg {
   int ctas_per_sm;
   uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_pub, o_ab, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
-  int* ws_cke;      // [B][NTmax]
+  int* ws_cke;      // [B][NTmax][W]
   long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [160][32][2] trace
 };
 
@@ -198,7 +198,7 @@ struct Smem {
   int* info;        // [0..GB) T_b, [kMaxGB..) L_b, [2*kMaxGB..) bad-label flags, [3*kMaxGB..) largest duplicate rank
   int* lab;         // [GB][Lpad]
   double* ckpt;     // [GB][NTmax][Lpad]   (or in the workspace)
-  int* cke;         // [GB][NTmax]
+  int* cke;         // [GB][NTmax][W] lane scales of the checkpoints
   float* ptile;     // [2][GB][PSEQ]
   double* s2;       // [2][GB]
   ChainPub* pub;    // [GB] alpha warp -> beta warp hand-over (W = 32)
@@ -212,22 +212,51 @@ struct Smem {
 // In both layouts position q of a direction's W lanes x NS states is state q for alpha and state Lpad-1-q for beta,
 // so both shift the same way.
 
-// rescale the NS states of each group of W lanes by the exact power of two of the group's largest value
-template <int NS, int W>
-__device__ __forceinline__ int rescale_group(double (&v)[NS]) {
-  double m = v[0];
+// ---- lane scales.  The states of a direction are spread over W lanes x NS states; they can differ by thousands of
+// binary orders of magnitude across the lattice (a model that is sure of one label for the whole sequence), far more
+// than the float64 range.  Every lane therefore carries its own exact power-of-two scale e_l (state = x * 2^e_l),
+// renewed once per tile, and the neighbour's state enters a lane through fac = 2^(e_{l-1} - e_l).
+constexpr int kSent = -(1 << 28);  // "no exponent": an all-zero lane
+// exact 2^e; 0 below the normal range, 2^1023 above
+__device__ __forceinline__ double pow2z(int e) {
+  if (e < -1022) return 0.0;
+  return __hiloint2double((1023 + min(e, 1023)) << 20, 0);
+}
+// exponent field - 1023 of the largest of NS non-negative values; kSent if that is zero / denormal / not finite
+template <int NS>
+__device__ __forceinline__ int top_exponent(const double (&v)[NS]) {
+  int hi = __double2hiint(v[0]);
 #pragma unroll
-  for (int j = 1; j < NS; ++j) m = fmax(m, v[j]);
-  int hi = __double2hiint(m);  // values are >= 0, so the high word orders like the value
+  for (int j = 1; j < NS; ++j) hi = max(hi, __double2hiint(v[j]));
+  const int ef = hi >> 20;
+  return (ef > 0 && ef < 0x7ff) ? ef - 1023 : kSent;
+}
+// Largest scale step between neighbouring lanes for tiles of TT steps: mass crosses at most ceil(TT/NS) lanes between
+// two rescales and gains 2^DEC of scaled magnitude per crossing at worst, which must stay inside the float64 range.
+template <int NS, int TT>
+struct LaneDec {
+  static constexpr int value = (TT + NS - 1) / NS >= 4 ? 208 : (TT + NS - 1) / NS >= 2 ? 420 : 850;
+};
+// New lane scale e_l = max_{k<=l}(A_k - DEC (l-k)), A_k = absolute exponent of lane k's largest state: every lane is
+// scaled to its own magnitude unless mass from a much larger lane upstream is about to arrive (mass only moves to
+// higher positions).  Values that fall 2^-1022 below the lane scale flush to zero; they are below float64 resolution
+// of what that mass turns them into.
+template <int NS, int W, int DEC>
+__device__ __forceinline__ void lane_rescale(double (&x)[NS], int& e, double& fac, int hl) {
+  const int te = top_exponent<NS>(x);
+  int env = te == kSent ? kSent : e + te;
 #pragma unroll
-  for (int o = W / 2; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-  const int ex = hi >> 20;
-  if (ex == 0 || ex >= 0x7ff) return 0;
-  const int e = ex - 1023;
-  const double sc = __hiloint2double((1023 - e) << 20, 0);  // exact 2^-e
+  for (int o = 1; o < W; o <<= 1) {
+    const int sh = __shfl_up_sync(0xffffffffu, env, o, W);
+    if (hl >= o && sh > kSent / 2) env = max(env, sh - DEC * o);
+  }
+  const int en = env > kSent / 2 ? env : e;
+  const double sc = pow2z(e - en);
 #pragma unroll
-  for (int j = 0; j < NS; ++j) v[j] *= sc;
-  return e;
+  for (int j = 0; j < NS; ++j) x[j] *= sc;
+  e = en;
+  const int eu = __shfl_up_sync(0xffffffffu, en, 1, W);
+  fac = hl == 0 ? 0.0 : pow2z(eu - en);
 }
 
 // emissions of the lane's NS states for one row of a p-tile, in the lane's own state order (rev: beta)
@@ -254,24 +283,28 @@ __device__ __forceinline__ void load_p(const float* row, int hl, bool rev, doubl
 // dependent path of a step is one shuffle + one DFMA for the lane's first state and one DFMA for the others
 // (a shuffle, a DADD and a DMUL in the textbook form).  alpha: x = alpha (NoBlankCTC.py:73-85).  beta:
 // x(s) = beta_t(s) p_t(s) and, with kSum, sum(s) = x(s) + x(s-1) = beta_t(s) (off the dependent path).
-// kFirst: first step of a tile -- `carry` enters position 0 of the direction (the virtual start state:
-// NoBlankCTC.py:92-93 and the t>0 guard at :75); in every other step position 0 of lane 0 has no neighbour.
+// fac = 2^(e_neighbour - e_lane) brings the neighbour lane's last state into this lane's scale (0 for the first lane
+// of a direction, whose shuffle returns its own finite value).
+// kFirst: first step of a tile -- `carry` enters position 0 of the direction, in the lane's own scale (the virtual
+// start state: NoBlankCTC.py:92-93 and the t>0 guard at :75).
 template <int NS, int W, bool kSum, bool kFirst>
-__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry) {
+__device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry, double fac) {
   double t[NS];
 #pragma unroll
   for (int j = 0; j < NS; ++j) t[j] = x[j] * p[j];
   double up = __shfl_up_sync(0xffffffffu, x[NS - 1], 1, W);
-  double p0 = p[0];
+  double f0 = fac;
   if (kFirst) {
-    if (hl == 0) up = carry;
-  } else {
-    if (hl == 0) p0 = 0.0;  // lane 0's shuffle result is its own (finite) value: times 0
+    if (hl == 0) {
+      up = carry;
+      f0 = 1.0;
+    }
   }
+  const double p0 = p[0] * f0;
   if (kSum) {
 #pragma unroll
     for (int j = NS - 1; j >= 1; --j) sum[j] = x[j] + x[j - 1];
-    sum[0] = x[0] + ((kFirst || hl != 0) ? up : 0.0);
+    sum[0] = fma(up, f0, x[0]);
   }
 #pragma unroll
   for (int j = NS - 1; j >= 1; --j) x[j] = fma(x[j - 1], p[j], t[j]);
@@ -280,29 +313,30 @@ __device__ __forceinline__ void chain_step(double (&x)[NS], double (&sum)[NS], c
 // run-time `first` (generic loops)
 template <int NS, int W, bool kSum>
 __device__ __forceinline__ void chain_step_rt(double (&x)[NS], double (&sum)[NS], const double (&p)[NS], int hl, double carry,
-                                              bool first) {
-  if (first) chain_step<NS, W, kSum, true>(x, sum, p, hl, carry);
-  else chain_step<NS, W, kSum, false>(x, sum, p, hl, 0.0);
+                                              double fac, bool first) {
+  if (first) chain_step<NS, W, kSum, true>(x, sum, p, hl, carry, fac);
+  else chain_step<NS, W, kSum, false>(x, sum, p, hl, 0.0, fac);
 }
 
 // Chain-warp state lives in plain registers of the kernel body (passed by reference to force-inlined functions).
 struct ChainScal {
-  double carry, zinv;
-  int Ea, Eb, Ez;
+  double carry, zinv, fac;
+  int e, Ez;  // this lane's scale; exponent of Z
 };
 
-// ---- phase 1, tile k: alpha over the tile's steps (W = 16: lanes 16-31 carry zeros)
+// ---- phase 1, tile k: alpha over the tile's steps (W = 16: lanes 16-31 carry zeros).  Checkpoint of tile k: the
+// states ck[(k*NS+j)*W] and the lane scales cke[k*W + lane].
 template <int NS, int W, int TT, int PS>
 __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int lane, int Tb, double* ck, int* cke, int k,
                                              const float* __restrict__ pt) {
   const int hl = lane & (W - 1);
   double sum[NS];
   if (k > 0) {
-    c.Ea += rescale_group<NS, W>(x);
+    lane_rescale<NS, W, LaneDec<NS, TT>::value>(x, c.e, c.fac, hl);
     if (lane < W) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) ck[(k * NS + j) * W] = x[j];
-      if (lane == 0) cke[k] = c.Ea;
+      cke[k * W + lane] = c.e;
     }
   }
   const int nv = min(TT, Tb - k * TT);
@@ -313,15 +347,15 @@ __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int 
     for (int i = 0; i < TT; ++i) load_p<NS, W>(pt + i * PS, hl, false, pr[i]);
 #pragma unroll
     for (int i = 0; i < TT; ++i) {
-      if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry);
-      else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0);
+      if (i == 0) chain_step<NS, W, false, true>(x, sum, pr[i], hl, c.carry, c.fac);
+      else chain_step<NS, W, false, false>(x, sum, pr[i], hl, 0.0, c.fac);
     }
   } else {
 #pragma unroll 2
     for (int i = 0; i < nv; ++i) {
       double pf[NS];
       load_p<NS, W>(pt + i * PS, hl, false, pf);
-      chain_step_rt<NS, W, false>(x, sum, pf, hl, c.carry, i == 0);
+      chain_step_rt<NS, W, false>(x, sum, pf, hl, c.carry, c.fac, i == 0);
     }
   }
   c.carry = 0.0;
@@ -332,7 +366,8 @@ __device__ __forceinline__ void chain_phase1(double (&x)[NS], ChainScal& c, int 
 template <int NS, int W>
 __device__ __forceinline__ void chain_beta_init(double (&x)[NS], ChainScal& c, int hl, int Lb) {
   constexpr int Lpad = W * NS;
-  c.Eb = 0;
+  c.e = 0;
+  c.fac = hl == 0 ? 0.0 : 1.0;
 #pragma unroll
   for (int j = 0; j < NS; ++j) x[j] = (Lpad - 1 - (hl * NS + j) == Lb) ? 1.0 : 0.0;
   c.carry = (hl == 0 && Lb == Lpad) ? 1.0 : 0.0;
@@ -350,13 +385,19 @@ __device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int
   double mine = x[0];
 #pragma unroll
   for (int j = 1; j < NS; ++j) mine = (rj >= j) ? x[j] : mine;
-  const double zhat = __shfl_sync(0xffffffffu, mine, sl / NS);
-  c.Ez = __shfl_sync(0xffffffffu, c.Ea, 0);
-  if (lane == 0) *loss_out = (zhat > 0.0) ? (float)(-(log(zhat) + (double)c.Ez * 0.6931471805599453)) : INFINITY;
-  c.zinv = (zhat > 0.0) ? (double)wgt / zhat : 0.0;  // sequence weight folded into gamma
+  double zhat = __shfl_sync(0xffffffffu, mine, sl / NS);
+  c.Ez = __shfl_sync(0xffffffffu, c.e, sl / NS);
+  // normalise to [1, 2): the lane's states may have shrunk since its last rescale
+  const int ezf = __double2hiint(zhat) >> 20;
+  const bool ok = zhat > 0.0 && ezf > 0 && ezf < 0x7ff;
+  if (ok) {
+    zhat *= pow2z(1023 - ezf);
+    c.Ez += ezf - 1023;
+  }
+  if (lane == 0) *loss_out = ok ? (float)(-(log(zhat) + (double)c.Ez * 0.6931471805599453)) : INFINITY;
+  c.zinv = ok ? (double)wgt / zhat : 0.0;  // sequence weight folded into gamma
   if (W == 16) {
     if (lane >= 16) chain_beta_init<NS, W>(x, c, hl, Lb);
-    else c.Eb = 0;
   } else if (lane == 0) {
     pub->zinv = c.zinv;
     pub->Ez = c.Ez;
@@ -364,30 +405,30 @@ __device__ __forceinline__ void chain_readout(double (&x)[NS], ChainScal& c, int
   }
 }
 
-// ---- phase 2, tile k: beta (isb) / alpha replay (!isb) from the checkpoint (ckv, exponent EaK; unused for
-// k = 0); alpha_t(s), beta_t(s) -> ab tile.  Eb_all: the beta direction's accumulated exponent.
+// ---- phase 2, tile k: beta (isb) / alpha replay (!isb) from the checkpoint (states ckv; eck = the checkpoint's
+// scale of this lane for the alpha direction, of the alpha lane that holds the same states for the beta direction;
+// unused for k = 0).  ab tile: alpha_t(s) in the alpha lane's scale, and beta_t(s) 2^(e_beta + e_alpha - Ez) w / Zhat,
+// so that gamma_t(s) = alpha-entry * beta-entry for the row warps.  (The beta entry is kept finite: where the alpha
+// entry has flushed to zero -- a state far below the mass arriving from upstream -- gamma is 0, not 0 * inf.)
 template <int NS, int W, int TT, int PS, int AS>
-__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, bool isb, int Eb_all, int Tb,
-                                             const double (&ckv)[NS], int EaK, int k, const float* __restrict__ pt,
-                                             double* __restrict__ abt, double* s2_out) {
+__device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int lane, bool isb, int Tb, const double (&ckv)[NS],
+                                             int eck, int k, const float* __restrict__ pt, double* __restrict__ abt) {
   constexpr int Lpad = W * NS;
   const int hl = lane & (W - 1);
   double sum[NS];
-  // gamma = alpha * beta * w / Z; the power-of-two part is split over both factors (range safety)
-  const int d = EaK + Eb_all - c.Ez;
-  const double s1 = pow2i(d / 2);
-  const double s2 = -(pow2i(d - d / 2) * c.zinv);  // negative: the row warps ADD gamma' = -w*gamma to the softmax row
-  if (lane == 0 && !isb) *s2_out = s2;
   if (!isb) {
-    if (k == 0) {
+    // alpha replay: from the virtual start state (k = 0) or the checkpoint
+    c.e = k == 0 ? 0 : eck;
+    c.carry = (k == 0 && hl == 0) ? 1.0 : 0.0;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) x[j] = 0.0;
-      c.carry = (lane == 0) ? s1 : 0.0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) x[j] = ckv[j] * s1;  // exact: alpha replay runs pre-scaled
-    }
+    for (int j = 0; j < NS; ++j) x[j] = k == 0 ? 0.0 : ckv[j];
   }
+  {
+    // (every lane takes part in the shuffle; the beta direction keeps its own fac)
+    const int eu = __shfl_up_sync(0xffffffffu, c.e, 1, W);
+    if (!isb) c.fac = hl == 0 ? 0.0 : pow2z(eu - c.e);
+  }
+  const double bs = isb ? pow2z(c.e + (k == 0 ? 0 : eck) - c.Ez) * c.zinv : 1.0;
   const int nv = min(TT, Tb - k * TT);
   // position -> state index of this lane's slots
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
@@ -400,10 +441,10 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
 #pragma unroll
     for (int jj = 0; jj < TT; ++jj) {
       const int i = isb ? (TT - 1 - jj) : jj;  // alpha walks up the tile, beta walks down
-      if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry);
-      else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0);
+      if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry, c.fac);
+      else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0, c.fac);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
+      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
     }
   } else {
 #pragma unroll 2
@@ -411,15 +452,20 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
       const int i = isb ? (nv - 1 - jj) : jj;
       double pf[NS];
       load_p<NS, W>(pt + i * PS, hl, isb, pf);
-      chain_step_rt<NS, W, true>(x, sum, pf, hl, c.carry, jj == 0);
+      chain_step_rt<NS, W, true>(x, sum, pf, hl, c.carry, c.fac, jj == 0);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? sum[j] : x[j];
+      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
     }
   }
   c.carry = 0.0;
   // every lane takes part in the group-wide shuffles; only the beta direction keeps the result
-  const int e = rescale_group<NS, W>(x);
-  if (isb) c.Eb += e;
+  int e2 = c.e;
+  double f2 = c.fac;
+  lane_rescale<NS, W, LaneDec<NS, TT>::value>(x, e2, f2, hl);
+  if (isb) {
+    c.e = e2;
+    c.fac = f2;
+  }
 }
 
 // ============================================================================ row warps
@@ -701,10 +747,10 @@ struct Rows {
   }
 
   // ---------------------------------------------------------------- phase 2 behind: gamma scatter into the slab
-  // abt: alpha/beta tiles of the item ([GB][ABSEQ]); s2v: per-sequence gamma scale (-w/Z and the tile exponents).
+  // abt: alpha/beta tiles of the item ([GB][ABSEQ]); their product is w*gamma (chain_phase2).
   // States that share a class are spread over rounds by their duplicate rank, so every round is a conflict-free
   // read-add-write on the row.
-  __device__ __forceinline__ void scatter_step(int t, unsigned char* tsl, const double* abt, const double* s2v) const {
+  __device__ __forceinline__ void scatter_step(int t, unsigned char* tsl, const double* abt) const {
     const bool live = t < Tb && wgt != 0.f;
     const RowGeom g = geom(t, tsl);
     float* yr = reinterpret_cast<float*>(g.srow) + g.off4;
@@ -712,11 +758,10 @@ struct Rows {
     if (live) {
       const double* at = abt + seq * G::ABSEQ + ti * AS;
       const double* bt = at + TT * AS;
-      const double s2 = s2v[seq];
 #pragma unroll
       for (int j = 0; j < NSL; ++j) {
         const int st = li + j * LPR;
-        gam[j] = label(j) >= 0 ? (float)(at[st] * (bt[st] * s2)) : 0.f;
+        gam[j] = label(j) >= 0 ? -(float)(at[st] * bt[st]) : 0.f;  // the row warps ADD gamma' = -w*gamma to the softmax
       }
     }
     const int nr = __reduce_max_sync(0xffffffffu, live ? max_rank : 0);
@@ -852,7 +897,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     const float wgt = (seq < gcnt) ? P.w_scalar * (P.seq_w ? P.seq_w[b0 + seq] : 1.f) : 0.f;
     double* ck = (cfg.ckpt_global ? cfg.ws_ckpt + ((size_t)min(b0 + seq, P.B - 1) * cfg.NTmax) * Lpad
                                   : S.ckpt + ((size_t)seq * cfg.NTmax) * Lpad) + (lane & (W - 1));  // [NTmax][CNS][W]
-    int* cke = cfg.ckpt_global ? cfg.ws_cke + (size_t)min(b0 + seq, P.B - 1) * cfg.NTmax : S.cke + (size_t)seq * cfg.NTmax;
+    int* cke = cfg.ckpt_global ? cfg.ws_cke + (size_t)min(b0 + seq, P.B - 1) * cfg.NTmax * W : S.cke + (size_t)seq * cfg.NTmax * W;  // [NTmax][W]
     ChainPub* pub = S.pub + seq;
     ChainScal chain;
     double cx[CNS];
@@ -860,7 +905,8 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     for (int j = 0; j < CNS; ++j) cx[j] = 0.0;
     chain.carry = (lane == 0) ? 1.0 : 0.0;
     chain.zinv = 0.0;
-    chain.Ea = 0; chain.Eb = 0; chain.Ez = 0;
+    chain.e = 0; chain.Ez = 0;
+    chain.fac = (lane & (W - 1)) == 0 ? 0.0 : 1.0;
     // ---- phase 1
     for (int it = -1; it < NTg; ++it) {
       if (!beta_warp && it >= 0 && it < NTb) {
@@ -874,18 +920,21 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     // ---- phase 2: item i = tile NTg-1-i
     if (want_grad) {
       double ckv[CNS];
-      int EaK = 0;
-      auto fetch_ckpt = [&](int k) {  // checkpoint of tile k (k = 0 starts from the virtual state instead)
+      int eck = 0;
+      // checkpoint of tile k (k = 0 starts from the virtual state instead): the alpha direction's states and lane
+      // scale; the beta direction takes the scale of the alpha lane that holds the same states
+      const int ecol = isb ? W - 1 - (lane & (W - 1)) : (lane & (W - 1));
+      auto fetch_ckpt = [&](int k) {
         if (k > 0 && k < NTb) {
           if (!beta_warp) {
 #pragma unroll
             for (int j = 0; j < CNS; ++j) ckv[j] = ck[(k * CNS + j) * W];
           }
-          EaK = cke[k];
+          eck = cke[k * W + ecol];
         } else {
 #pragma unroll
           for (int j = 0; j < CNS; ++j) ckv[j] = 0.0;
-          EaK = 0;
+          eck = 0;
         }
       };
 #pragma unroll
@@ -903,14 +952,12 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
             double ckc[CNS];
 #pragma unroll
             for (int j = 0; j < CNS; ++j) ckc[j] = ckv[j];
-            const int EaC = EaK;
+            const int ecc = eck;
             fetch_ckpt(k - 1);  // in flight while this tile runs
             const int buf = i & 1;
-            const int Eb_all = NCW == 2 ? (beta_warp ? chain.Eb : pub->Eb) : __shfl_sync(0xffffffffu, chain.Eb, 16);
-            PROF_SCOPE(1, chain_phase2<CNS, W, TT, PS, AS>(cx, chain, lane, isb, Eb_all, Tb, ckc, EaC, k,
+            PROF_SCOPE(1, chain_phase2<CNS, W, TT, PS, AS>(cx, chain, lane, isb, Tb, ckc, ecc, k,
                                                            S.ptile + (size_t)(buf * GB + seq) * G::PSEQ,
-                                                           S.ab + (size_t)(buf * GB + seq) * G::ABSEQ, &S.s2[buf * GB + seq]))
-            if (beta_warp && lane == 0) pub->Eb = chain.Eb;  // read by the alpha warp after the barrier
+                                                           S.ab + (size_t)(buf * GB + seq) * G::ABSEQ))
           } else {
             fetch_ckpt(k - 1);
           }
@@ -960,7 +1007,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
         if (ib >= 0 && ib < NTg) {
           const int tb = (NTg - 1 - ib) * TT + ti;
           if (tb < Tg) {
-            PROF_SCOPE(5, rows.scatter_step(tb, rows.slab(slot_b), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ, S.s2 + (ib & 1) * GB))
+            PROF_SCOPE(5, rows.scatter_step(tb, rows.slab(slot_b), S.ab + (size_t)((ib & 1) * GB) * G::ABSEQ))
             fence_proxy_async();
           }
           slot_b = slot_b + 1 == NSLOT ? 0 : slot_b + 1;

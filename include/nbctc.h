@@ -49,8 +49,10 @@ extern "C" {
                                      then omits the room for the unaligned-tensor fallback (the call fails with
                                      NBCTC_ERR_INVALID_ARG if the promise is broken) */
 
-#define NBCTC_FLAG_LOCKSTEP 8u    /* single-label variant: use the round-1 lock-step fused kernel instead of the
-                                     pipeline kernel (cross-check / comparison) */
+#define NBCTC_FLAG_LOCKSTEP 8u    /* single-label variant: the lock-step fused kernel (the default; stream_kernel.cuh) */
+#define NBCTC_FLAG_PIPELINE 16u   /* single-label variant: the pipeline kernel (pipe_kernel.cuh: ticket-scheduled row and
+                                     chain stages).  Without either flag the NBCTC_PATH environment variable
+                                     ("pipe" / "lockstep") decides, else the lock-step kernel */
 
 typedef void* nbctc_stream_t; /* cudaStream_t */
 

@@ -81,7 +81,7 @@ CTC_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+@pytest.mark.parametrize("flags", [0, 1, 16], ids=["default", "generic", "pipeline"])
 @pytest.mark.parametrize("shape", CTC_SHAPES, ids=lambda s: "T%d_B%d_C%d_L%d_%d%d" % s)
 def test_ctc_random_vs_oracle(nb, shape, flags):
     T, B, C, L, ragged, dup = shape
@@ -451,14 +451,15 @@ def test_bctc_tiled_path_last_row_ends_inside_a_chunk(nb):
         assert rel_l2(grad, ref["grad"]) < TOL
 
 
+@pytest.mark.parametrize("flags", [0, 16], ids=["lockstep", "pipeline"])
 @pytest.mark.parametrize("shape", [(19, 3, 7, 5), (23, 7, 157, 12), (16, 6, 66, 9), (9, 13, 5, 4), (40, 9, 1030, 20)],
                          ids=lambda s: "T%d_B%d_C%d_L%d" % s)
-def test_slab_alignment_phases(nb, shape):
+def test_slab_alignment_phases(nb, shape, flags):
     """B*C not a multiple of 4: the 16-byte phase of a time step's rows changes with t; partial last groups;
     tensors whose byte size is not a multiple of 16."""
     T, B, C, L = shape
     x, lab, il, tl = make_ctc_case(500 + T + C, T, B, C, L, ragged_T=True, dup=True)
-    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl)
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl, flags=flags)
     assert_parity(loss, grad, oracle("ctc", x, lab, il, tl))
 
 
