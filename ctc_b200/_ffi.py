@@ -29,6 +29,7 @@ SIGNATURES = {
     "nbctc_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _u32]),
     "nbctc_loss_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _u32, _vp]),
     "nbbctc_loss_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _u32, _vp]),
+    "nbctc_aux_ce_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "nbctc_scale_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "nbctc_best_path_i32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nbctc_best_path_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),

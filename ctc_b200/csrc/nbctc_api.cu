@@ -311,6 +311,22 @@ int nbbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C, c
   return run(p, true, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
 }
 
+int nbctc_aux_ce_f32(const float* logits, int64_t T, int64_t B, int64_t C, const int64_t* frame_index,
+                     const int64_t* input_lengths, const int32_t* class_index, const float* multi_hot, float alpha_weight,
+                     const float* seq_weights, float* ce_per_seq, float* grad_logits, nbctc_stream_t stream) {
+  clear_error();
+  if (T < 1 || B < 1 || C < 1 || !logits || !ce_per_seq || (!frame_index && !input_lengths)) {
+    set_error("invalid argument to nbctc_aux_ce_f32");
+    return NBCTC_ERR_INVALID_ARG;
+  }
+  if ((class_index == nullptr) == (multi_hot == nullptr)) {
+    set_error("nbctc_aux_ce_f32 takes exactly one of class_index and multi_hot");
+    return NBCTC_ERR_INVALID_ARG;
+  }
+  return aux_ce_launch(logits, T, B, C, frame_index, input_lengths, class_index, multi_hot, class_index ? 0 : 1, alpha_weight,
+                       seq_weights, ce_per_seq, grad_logits, static_cast<cudaStream_t>(stream));
+}
+
 int nbctc_scale_grad_f32(float* grad_logits, int64_t T, int64_t B, int64_t C, const float* grad_out, int per_seq,
                          nbctc_stream_t stream) {
   clear_error();

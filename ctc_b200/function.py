@@ -154,6 +154,90 @@ def no_blank_binary_ctc_loss(logits, targets, input_length, target_length, reduc
                                      flags, out64, want_grad)
 
 
+class _CtcPlusCeFunction(torch.autograd.Function):
+    """CTC + alpha * CE on one frame per sequence (train.py:353, models/__init__.py:85-86).
+
+    The CTC gradient comes from the fused kernel; ``nbctc_aux_ce_f32`` then ADDS alpha * d CE / d logits into the B rows
+    it touches, on the same stream.  Returns (total, ctc, ce) -- the three meters of train.py:439-441."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, input_length, target_length, ce_targets, alpha, frame_index, binary, total_batch,
+                flags, want_grad):
+        if not logits.is_cuda:
+            raise _ffi.NbctcError("ctc_b200 is CUDA-only: logits must be a CUDA tensor (there is no CPU fallback)")
+        T, B, C = logits.shape
+        dev = logits.device
+        x = logits.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        if binary:
+            tg = labels.detach().to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            tg = labels.detach().to(device=dev, dtype=torch.int32).contiguous()
+        il = _prep_lengths(input_length, dev, B, "input_length")
+        tl = _prep_lengths(target_length, dev, B, "target_length")
+        want_grad = bool(want_grad) and bool(ctx.needs_input_grad[0])
+        nb = int(total_batch) if total_batch else B
+        w = 1.0 / nb
+        per_seq, loss_sum, reduced, grad = _launch(x, tg, il, tl, binary, want_grad, w, None, int(flags))
+        ce_t = ce_targets.detach().to(device=dev)
+        if ce_t.dim() == 1:
+            if ce_t.shape[0] != B:
+                raise ValueError(f"class-index CE targets must be (B,)=({B},), got {tuple(ce_t.shape)}")
+            y_idx, y_hot = ce_t.to(torch.int32).contiguous(), None
+        else:
+            if tuple(ce_t.shape) != (B, C):
+                raise ValueError(f"multi-hot CE targets must be (B,C)=({B},{C}), got {tuple(ce_t.shape)}")
+            y_idx, y_hot = None, ce_t.to(torch.float32).contiguous()
+        fi = None if frame_index is None else _prep_lengths(frame_index, dev, B, "frame_index")
+        ce_per_seq = torch.empty(B, dtype=torch.float32, device=dev)
+        lib = _ffi.lib()
+        with _on_device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.nbctc_aux_ce_f32(x.data_ptr(), T, B, C, _ptr(fi), il.data_ptr(), _ptr(y_idx), _ptr(y_hot),
+                                      float(alpha) * w, None, ce_per_seq.data_ptr(), _ptr(grad), stream)
+        _ffi.check(rc, "nbctc_aux_ce_f32")
+        ce = ce_per_seq.sum() * w
+        ctx.grad = grad
+        ctx.in_dtype = logits.dtype
+        ctx.shape = (T, B, C)
+        ctx.mark_non_differentiable(reduced, ce)
+        return reduced + float(alpha) * ce, reduced, ce
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out, _g_ctc, _g_ce):
+        grad = ctx.grad
+        if grad is None:
+            raise RuntimeError("backward called twice (or without a gradient buffer); the fused gradient is consumed "
+                               "by the first backward")
+        ctx.grad = None
+        T, B, C = ctx.shape
+        go = grad_out.detach().to(device=grad.device, dtype=torch.float32).contiguous()
+        lib = _ffi.lib()
+        with _on_device(grad.device):
+            stream = torch.cuda.current_stream(grad.device).cuda_stream
+            rc = lib.nbctc_scale_grad_f32(grad.data_ptr(), T, B, C, go.data_ptr(), 0, stream)
+        _ffi.check(rc, "nbctc_scale_grad_f32")
+        if grad.dtype != ctx.in_dtype:
+            grad = grad.to(ctx.in_dtype)
+        return (grad,) + (None,) * 10
+
+
+def ctc_plus_cross_entropy(logits, labels, input_length, target_length, ce_targets, alpha, *, frame_index=None,
+                           binary=False, total_batch=None, flags=_ffi.FLAG_DEFAULT):
+    """``Loss = CTC + alpha * CE`` of the reference's trainer (opts.py:74 --alpha, train.py:353) in one pass over the
+    gradient: the CE is taken on the scores of ONE frame per sequence (``frame_index``, default ``input_length-1`` as
+    train.py:434 classifies ``v_output[temporal-1]``).  ``ce_targets``: (B,) class indices -> ``nn.CrossEntropyLoss``
+    (models/__init__.py:85); (B,C) multi-hot -> the reference's ``CrossEntropy`` module (CrossEntropy.py:17-32).
+    Both losses are means over the batch.  Returns ``(total, ctc, ce)``; only ``total`` carries a gradient."""
+    want_grad = torch.is_grad_enabled() and logits.requires_grad
+    return _CtcPlusCeFunction.apply(logits, labels, input_length, target_length, ce_targets, alpha, frame_index,
+                                    binary, total_batch, flags, want_grad)
+
+
 def best_path(logits, labels, input_length, target_length, want_argmax=True):
     """Viterbi alignment on the no-blank lattice + per-frame argmax.
 

@@ -107,6 +107,24 @@ int nbbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C,
                          nbctc_stream_t stream);
 
 /*
+ * Auxiliary cross-entropy on one frame per sequence.  The reference mixes its CTC loss with a
+ * cross-entropy weighted by --alpha (opts.py:74, main.py:42, train.py:353) on the scores of one frame per sequence
+ * (train.py:434: v_output[temporal-1]).  Exactly one of the two target forms is given:
+ *   class_index (B) int32     nn.CrossEntropyLoss (models/__init__.py:85):  ce_b = logsumexp(x) - x[y_b]
+ *   multi_hot (B,C) float32   the reference's CrossEntropy module (CrossEntropy.py:17-32): q = softmax(x),
+ *                             ce_b = log sum_c exp(q_c) - sum_{n: multi_hot[b][n] == 1} q_n
+ * x = logits[t_b, b, :], t_b = frame_index[b], or input_lengths[b]-1 when frame_index is NULL.
+ * ce_per_seq[b] receives ce_b; when grad_logits != NULL, alpha_weight * seq_weights[b] * d ce_b / d x is ADDED to the
+ * row (t_b, b) of grad_logits -- call it on the stream of, and after, *_loss_grad_f32, with
+ * alpha_weight = alpha * weight_scalar (the reference averages both losses over the batch): the sum is the gradient
+ * of CTC + alpha * CE.  B rows of the T*B are touched.  Sequences with t_b outside [0,T) or a class index outside
+ * [0,C) get ce = +inf and no gradient.
+ */
+int nbctc_aux_ce_f32(const float* logits, int64_t T, int64_t B, int64_t C, const int64_t* frame_index,
+                     const int64_t* input_lengths, const int32_t* class_index, const float* multi_hot, float alpha_weight,
+                     const float* seq_weights, float* ce_per_seq, float* grad_logits, nbctc_stream_t stream);
+
+/*
  * Backward-time rescale of a gradient produced by *_loss_grad_f32 with the upstream
  * gradient that autograd hands to backward() (train.py:444).  grad[t,b,c] *= g where
  * g = grad_out[0] (per_seq == 0) or grad_out[b] (per_seq != 0).  When per_seq == 0 and

@@ -254,3 +254,39 @@ def frame_argmax(logits):
     """Per-frame argmax class, ties -> lowest index (train.py:41-56 uses topk on logits)."""
     x = np.asarray(logits)
     return np.argmax(x, axis=2).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Auxiliary cross-entropy on one frame per sequence (SURVEY 8(f4)): the reference mixes the CTC loss with a
+# cross-entropy on the last frame's scores, weighted by --alpha (opts.py:74, main.py:42, train.py:353).
+#   mode "index":    nn.CrossEntropyLoss on class indices (models/__init__.py:85):  ce_b = lse(x_b) - x_b[y_b]
+#   mode "multihot": the reference's own CrossEntropy module (CrossEntropy.py:17-32) on multi-hot targets:
+#                    q = softmax(x_b) (:22); ce_b = log sum_c exp(q_c) (:25) - sum_{n: target[b][n] == 1} q_n (:26-29)
+# Both are averaged over the batch (CrossEntropy.py:30; nn.CrossEntropyLoss default reduction).
+def aux_ce(logits, targets, frame_index, mode="index", reduction="mean"):
+    """logits (T,B,C); frame_index (B) = the frame whose scores are classified (train.py:434 uses temporal-1);
+    targets (B,) class indices or (B,C) multi-hot.  Returns dict(loss, per_seq, grad) with grad = d loss / d logits
+    (zero outside the B classified rows)."""
+    x = _as_f64(logits)
+    T, B, C = x.shape
+    fi = _as_i64(frame_index)
+    rows = x[fi, np.arange(B)]                                  # (B,C)
+    q = np.exp(log_softmax(rows))
+    if mode == "index":
+        y = _as_i64(targets)
+        per = -log_softmax(rows)[np.arange(B), y]
+        g_rows = q.copy()
+        g_rows[np.arange(B), y] -= 1.0
+    elif mode == "multihot":
+        pos = (_as_f64(targets) == 1.0)                         # CrossEntropy.py:28 tests equality with 1
+        eq = np.exp(q)
+        S = eq.sum(axis=1)
+        per = np.log(S) - (q * pos).sum(axis=1)
+        g = eq / S[:, None] - pos                               # d per / d q
+        g_rows = q * (g - (g * q).sum(axis=1, keepdims=True))   # through the softmax
+    else:
+        raise ValueError(mode)
+    loss, w = _reduce(per, B, reduction)
+    grad = np.zeros_like(x)
+    grad[fi, np.arange(B)] = g_rows * w[:, None]
+    return dict(loss=loss, per_seq=per, grad=grad)

@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("metrics_"))
+                  if not os.path.basename(p).startswith(("metrics_", "ce_")))
 
 
 def load_golden(name):
