@@ -17,6 +17,7 @@ FLAG_NO_GRAD = 2
 FLAG_ALIGNED16 = 4
 FLAG_LOCKSTEP = 8
 FLAG_PIPELINE = 16
+FLAG_SEQWARP = 32
 
 _lib = None
 
@@ -28,6 +29,7 @@ SIGNATURES = {
     "nbctc_kernel_launch_count": (C.c_uint64, []),
     "nbctc_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _u32]),
     "nbctc_loss_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _u32, _vp]),
+    "nbctc_loss_grad_lse_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _u32, _vp]),
     "nbbctc_loss_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _u32, _vp]),
     "nbctc_aux_ce_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "nbctc_scale_grad_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp]),

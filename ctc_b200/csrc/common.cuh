@@ -76,6 +76,11 @@ bool pipe_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 size_t pipe_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// sequence-per-warp path of the single-label variant (nbctc_seqwarp.cu: one warp per sequence, whole batch in flight)
+bool seqwarp_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+size_t seqwarp_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row_lse_in, float* row_lse_out, cudaStream_t stream);
+
 // auxiliary cross-entropy on one frame per sequence, added into the gradient rows (nbctc_auxce.cu)
 int aux_ce_launch(const float* logits, int64_t T, int64_t B, int64_t C, const int64_t* frame_index, const int64_t* in_len,
                   const int32_t* y_index, const float* y_multihot, int mode, float alpha_w, const float* seq_w, float* ce_per_seq,

@@ -48,14 +48,25 @@ __global__ void scale_grad_kernel(float* __restrict__ g, int64_t n_vec4, int64_t
 
 // which fused single-label kernel: NBCTC_FLAG_PIPELINE / NBCTC_FLAG_LOCKSTEP, else the NBCTC_PATH environment variable
 // ("pipe" | "lockstep", read once), else the lock-step kernel
-bool want_pipeline(uint32_t flags) {
-  if (flags & NBCTC_FLAG_PIPELINE) return true;
-  if (flags & NBCTC_FLAG_LOCKSTEP) return false;
+int env_path() {  // 0 none, 1 "pipe", 2 "lockstep", 3 "seqwarp"
   static const int env = [] {
     const char* v = getenv("NBCTC_PATH");
-    return (v && v[0] == 'p') ? 1 : 0;
+    return !v ? 0 : v[0] == 'p' ? 1 : v[0] == 'l' ? 2 : v[0] == 's' ? 3 : 0;
   }();
-  return env != 0;
+  return env;
+}
+constexpr uint32_t kPathFlags = NBCTC_FLAG_PIPELINE | NBCTC_FLAG_LOCKSTEP | NBCTC_FLAG_SEQWARP;
+bool want_pipeline(uint32_t flags) {
+  if (flags & kPathFlags) return (flags & NBCTC_FLAG_PIPELINE) != 0;
+  return env_path() == 1;
+}
+// the sequence-per-warp kernel: on request, else for batches that fill the GPU with one sequence per warp (the
+// lock-step kernel keeps the small batches: it spreads ONE sequence over a whole CTA)
+bool want_seqwarp(uint32_t flags, int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  if (!seqwarp_supported(T, B, C, Lmax)) return false;
+  if (flags & kPathFlags) return (flags & NBCTC_FLAG_SEQWARP) != 0;
+  if (env_path()) return env_path() == 3;
+  return B >= 2048;
 }
 
 int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void* tg, int64_t Lmax,
@@ -75,9 +86,21 @@ int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void
   return NBCTC_OK;
 }
 
-int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t stream) {
+int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t stream, const float* row_lse_in = nullptr,
+        float* row_lse_out = nullptr) {
   if (flags & NBCTC_FLAG_NO_GRAD) p.grad = nullptr;
   int rc;
+  const bool use_sw = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_seqwarp(flags, p.T, p.B, p.C, p.Lmax);
+  if ((row_lse_in || row_lse_out) && !use_sw) {
+    set_error("row_lse needs the sequence-per-warp kernel (single-label variant, C <= 256, Lmax <= 64)");
+    return NBCTC_ERR_UNSUPPORTED;
+  }
+  if (use_sw) {
+    rc = seqwarp_launch(p, ws, ws_bytes, row_lse_in, row_lse_out, stream);
+    if (rc != NBCTC_OK) return rc;
+    if (p.loss_sum || p.loss_reduced) rc = reduce_loss_launch(p, stream);
+    return rc;
+  }
   const bool shape_ok = !(flags & NBCTC_FLAG_GENERIC) && fused_supported(p.T, p.B, p.C, p.Lmax, binary);
   if (shape_ok && (flags & NBCTC_FLAG_ALIGNED16) && !fused_pointers_ok(p)) {
     set_error("NBCTC_FLAG_ALIGNED16 was passed but logits / grad_logits are not 16-byte aligned");
@@ -274,6 +297,7 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   size_t f = 0;
   if (fused_supported(T, B, C, Lmax, binary != 0)) f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
   if (!binary && want_pipeline(flags) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
+  if (!binary && want_seqwarp(flags, T, B, C, Lmax)) return seqwarp_workspace_bytes(T, B, C, Lmax);  // any alignment
   if (f) return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
   if (binary && tiled_bin_supported(T, B, C, Lmax)) return align_up(g, 256) + tiled_bin_workspace_bytes(T, B, C, Lmax);
   return g;
@@ -293,6 +317,23 @@ int nbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C, co
   p.seq_w = seq_weights; p.w_scalar = weight_scalar;
   p.T = T; p.B = B; p.C = C; p.Lmax = Lmax;
   return run(p, false, workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
+}
+
+int nbctc_loss_grad_lse_f32(const float* logits, int64_t T, int64_t B, int64_t C, const int32_t* labels, int64_t Lmax,
+                            const int64_t* input_lengths, const int64_t* target_lengths, const float* row_lse_in, float* row_lse_out,
+                            float* loss_per_seq, double* loss_sum, float* loss_reduced, float* grad_logits, const float* seq_weights,
+                            float weight_scalar, void* workspace, size_t workspace_bytes, uint32_t flags, nbctc_stream_t stream) {
+  clear_error();
+  int rc = check_common(logits, T, B, C, labels, Lmax, input_lengths, target_lengths, loss_per_seq);
+  if (rc != NBCTC_OK) return rc;
+  Problem p{};
+  p.logits = logits; p.labels = labels; p.targets = nullptr;
+  p.in_len = input_lengths; p.tgt_len = target_lengths;
+  p.loss = loss_per_seq; p.loss_sum = loss_sum; p.loss_reduced = loss_reduced; p.grad = grad_logits;
+  p.seq_w = seq_weights; p.w_scalar = weight_scalar;
+  p.T = T; p.B = B; p.C = C; p.Lmax = Lmax;
+  return run(p, false, workspace, workspace_bytes, (flags & ~kPathFlags) | NBCTC_FLAG_SEQWARP, static_cast<cudaStream_t>(stream),
+             row_lse_in, row_lse_out);
 }
 
 int nbbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C, const float* targets, int64_t Lmax,

@@ -1,0 +1,146 @@
+// Host side of the sequence-per-warp kernel (seqwarp_kernel.cuh): shape gate, workspace carve-up, the longest-first
+// work queue for batches larger than one wave (the north star's "length-bucketed launch fusion": ONE launch, the
+// sequences sorted into 256 length buckets on the device and handed to the persistent warps longest first), dispatch.
+//
+// Algorithmic HBM bytes per launch: 2*4*T*B*C (logits read once, gradient written once).  The kernel itself moves
+// 3*4*T*B*C (the logits are read again in phase 2) + 4 bytes per row of log-partitions + one 8-byte alpha
+// checkpoint per state and 4 steps, both ways.
+#include <algorithm>
+
+#include "seqwarp_kernel.cuh"
+
+namespace nbctc {
+namespace {
+
+constexpr int kPrepThreads = 1024;
+constexpr int kBins = 256;
+
+// order[] = sequences by descending input length (256 buckets; ascending b inside a bucket up to the scheduling of
+// one chunk of 1024 threads -- the order only steers the work queue, never the results); ticket = 0
+__global__ void __launch_bounds__(kPrepThreads) seqwarp_prep_kernel(const int64_t* __restrict__ in_len, int B, int T, int* __restrict__ order,
+                                                                     int* __restrict__ ticket) {
+  __shared__ int hist[kBins];
+  __shared__ int cursor[kBins];
+  for (int i = threadIdx.x; i < kBins; i += kPrepThreads) hist[i] = 0;
+  __syncthreads();
+  auto bin_of = [&](int b) {
+    int64_t tb = in_len[b];
+    tb = tb < 0 ? 0 : tb > T ? T : tb;
+    return (int)(((int64_t)(T - tb) * (kBins - 1)) / (T > 0 ? T : 1));
+  };
+  for (int b = threadIdx.x; b < B; b += kPrepThreads) atomicAdd(&hist[bin_of(b)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < kBins; ++i) {
+      cursor[i] = acc;
+      acc += hist[i];
+    }
+    *ticket = 0;
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += kPrepThreads) {
+    const int b = b0 + threadIdx.x;
+    if (b < B) order[atomicAdd(&cursor[bin_of(b)], 1)] = b;
+    __syncthreads();
+  }
+}
+
+struct SwPlan {
+  bool ok;
+  int NS, EPL, K, Tp;
+  size_t o_order, o_lse, o_ckx, o_cke, bytes;
+};
+
+SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  SwPlan pl{};
+  if (T < 1 || B < 1 || C < 1 || Lmax < 1 || Lmax > 64 || C > 256 || T > (1 << 24) || B > (1 << 24)) return pl;
+  if (T * B * C >= ((int64_t)1 << 40)) return pl;
+  pl.NS = Lmax <= 32 ? 1 : 2;
+  pl.EPL = (int)((C + 31) / 32);
+  pl.K = (int)((T + 3) / 4);
+  pl.Tp = pl.K * 4;
+  size_t off = 256;
+  pl.o_order = off;
+  off = align_up(off + sizeof(int) * (size_t)B, 256);
+  pl.o_lse = off;
+  off = align_up(off + sizeof(float) * (size_t)B * pl.Tp, 256);
+  pl.o_ckx = off;
+  off = align_up(off + sizeof(double) * (size_t)B * pl.K * 32 * pl.NS, 256);
+  pl.o_cke = off;
+  off = align_up(off + sizeof(int) * (size_t)B * (pl.K / 2 + 1) * 32, 256);
+  pl.bytes = off;
+  pl.ok = true;
+  return pl;
+}
+
+int g_sms = 0;
+int g_blocks_per_sm[3] = {0, 0, 0};
+
+}  // namespace
+
+bool seqwarp_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax) { return make_plan(T, B, C, Lmax).ok; }
+
+size_t seqwarp_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
+  const SwPlan pl = make_plan(T, B, C, Lmax);
+  return pl.ok ? pl.bytes : 256;
+}
+
+int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row_lse_in, float* row_lse_out, cudaStream_t stream) {
+  const SwPlan pl = make_plan(p.T, p.B, p.C, p.Lmax);
+  if (!pl.ok) {
+    set_error("shape not supported by the sequence-per-warp kernel");
+    return NBCTC_ERR_UNSUPPORTED;
+  }
+  if (ws == nullptr || ws_bytes < pl.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", pl.bytes, ws_bytes);
+    return NBCTC_ERR_WORKSPACE;
+  }
+  if (g_sms == 0) {
+    int dev = 0;
+    NBCTC_CUDA_CHECK(cudaGetDevice(&dev));
+    NBCTC_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  char* w = static_cast<char*>(ws);
+  SwParams P{};
+  P.p = p;
+  P.lse2 = reinterpret_cast<float*>(w + pl.o_lse);
+  P.ckx = reinterpret_cast<double*>(w + pl.o_ckx);
+  P.cke = reinterpret_cast<int*>(w + pl.o_cke);
+  P.row_lse_in = row_lse_in;
+  P.row_lse_out = row_lse_out;
+  P.K = pl.K;
+  P.Tp = pl.Tp;
+  const int per_sm = seqwarp_ctas_per_sm(pl.NS);
+  const int64_t resident = (int64_t)per_sm * g_sms;  // CTAs of one warp
+  const int64_t need = p.B;
+  int grid;
+  if (need <= resident) {
+    grid = (int)need;  // the whole batch is one wave: warp = sequence
+  } else {
+    grid = (int)resident;
+    P.ticket = reinterpret_cast<int*>(w);
+    P.order = reinterpret_cast<int*>(w + pl.o_order);
+    seqwarp_prep_kernel<<<1, kPrepThreads, 0, stream>>>(p.in_len, (int)p.B, (int)p.T, const_cast<int*>(P.order), P.ticket);
+    NBCTC_LAUNCH_CHECK();
+  }
+  return launch_seqwarp(P, pl.NS, pl.EPL, grid, stream);
+}
+
+int launch_seqwarp(const SwParams& P, int NS, int EPL, int grid, cudaStream_t stream) {
+  switch (EPL) {
+    case 1: return launch_seqwarp_epl<1>(P, NS, grid, stream);
+    case 2: return launch_seqwarp_epl<2>(P, NS, grid, stream);
+    case 3: return launch_seqwarp_epl<3>(P, NS, grid, stream);
+    case 4: return launch_seqwarp_epl<4>(P, NS, grid, stream);
+    case 5: return launch_seqwarp_epl<5>(P, NS, grid, stream);
+    case 6: return launch_seqwarp_epl<6>(P, NS, grid, stream);
+    case 7: return launch_seqwarp_epl<7>(P, NS, grid, stream);
+    case 8: return launch_seqwarp_epl<8>(P, NS, grid, stream);
+    default: set_error("seqwarp: EPL=%d not built", EPL); return NBCTC_ERR_UNSUPPORTED;
+  }
+}
+
+int seqwarp_ctas_per_sm(int NS) { return NS == 1 ? 28 : NS == 2 ? 20 : 12; }  // CTA = one warp
+
+}  // namespace nbctc

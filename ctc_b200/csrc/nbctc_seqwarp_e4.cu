@@ -1,0 +1,5 @@
+// explicit instantiation unit of the sequence-per-warp kernel: rows of 97..128 classes
+#include "seqwarp_kernel.cuh"
+namespace nbctc {
+template int launch_seqwarp_epl<4>(const SwParams&, int, int, cudaStream_t);
+}

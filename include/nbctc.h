@@ -54,6 +54,9 @@ extern "C" {
                                      chain stages).  Without either flag the NBCTC_PATH environment variable
                                      ("pipe" / "lockstep") decides, else the lock-step kernel */
 
+#define NBCTC_FLAG_SEQWARP 32u    /* single-label variant: the sequence-per-warp kernel (seqwarp_kernel.cuh; C <= 256,
+                                     Lmax <= 64): the default for batches of >= 2048 sequences */
+
 typedef void* nbctc_stream_t; /* cudaStream_t */
 
 /* Library version (NBCTC_VERSION of the build). */
@@ -105,6 +108,23 @@ int nbbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C,
                          float* grad_logits, const float* seq_weights, float weight_scalar,
                          void* workspace, size_t workspace_bytes, uint32_t flags,
                          nbctc_stream_t stream);
+
+/*
+ * nbctc_loss_grad_f32 with the row log-partitions exposed (the producer of the logits -- the
+ * reference's LSTM head, LSTM.py:39-51, train.py:417-427 -- can fuse log-softmax's row reduction into its own
+ * epilogue).  row_lse (T,B) float32 = log sum_c exp(logits[t,b,c]) (NoBlankCTC.py:136 is logits - row_lse):
+ *   row_lse_in  != NULL  the loss trusts it and phase 1 reads only the label entries of every row (about half the
+ *                        sectors of the logits instead of all of them);
+ *   row_lse_out != NULL  receives the log-partitions this call computed, rows t < input_lengths[b] only (e.g. for the
+ *                        next call on the same logits, or for a log-softmax consumer).
+ * Both may be NULL (then it is nbctc_loss_grad_f32 on the sequence-per-warp kernel).  Shapes outside that kernel's
+ * range (C > 256 or Lmax > 64) return NBCTC_ERR_UNSUPPORTED.
+ */
+int nbctc_loss_grad_lse_f32(const float* logits, int64_t T, int64_t B, int64_t C, const int32_t* labels, int64_t Lmax,
+                            const int64_t* input_lengths, const int64_t* target_lengths, const float* row_lse_in,
+                            float* row_lse_out, float* loss_per_seq, double* loss_sum, float* loss_reduced,
+                            float* grad_logits, const float* seq_weights, float weight_scalar, void* workspace,
+                            size_t workspace_bytes, uint32_t flags, nbctc_stream_t stream);
 
 /*
  * Auxiliary cross-entropy on one frame per sequence.  The reference mixes its CTC loss with a

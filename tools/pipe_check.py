@@ -70,7 +70,9 @@ def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
     if len(sys.argv) > 2 and sys.argv[2] == "lockstep":
         DEFAULT_FLAGS = _ffi.FLAG_LOCKSTEP
-    print("lock-step kernel;" if DEFAULT_FLAGS == _ffi.FLAG_LOCKSTEP else "split pipeline kernel;" if os.environ.get("NBCTC_PIPE_SPLIT") else "fused pipeline kernel;", torch.cuda.get_device_name(0), flush=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "seqwarp":
+        DEFAULT_FLAGS = _ffi.FLAG_SEQWARP
+    print("sequence-per-warp kernel;" if DEFAULT_FLAGS == _ffi.FLAG_SEQWARP else "lock-step kernel;" if DEFAULT_FLAGS == _ffi.FLAG_LOCKSTEP else "split pipeline kernel;" if os.environ.get("NBCTC_PIPE_SPLIT") else "fused pipeline kernel;", torch.cuda.get_device_name(0), flush=True)
     ok = True
     ok &= run("tiny T=4 B=2", *case(0, 4, 2, 157, 3, ragged=False))
     ok &= run("cfg1-like", *case(1, 64, 8, 157, 8, ragged=False))
@@ -81,9 +83,15 @@ def main():
     ok &= run("peaked 14 L<=32", *case(6, 256, 16, 157, 32, ragged=False, boost=14.0, Lmin=20))
     ok &= run("peaked 14 L<=64", *case(7, 512, 8, 157, 64, ragged=False, boost=14.0, Lmin=50))
     ok &= run("no grad", *case(8, 64, 12, 157, 32), want_grad=False)
+    ok &= run("dup heavy", *case(14, 70, 40, 6, 32, dup=True))
+    ok &= run("peaked 30 L<=32", *case(15, 256, 16, 157, 32, ragged=False, boost=30.0, Lmin=20))
+    ok &= run("C=33 odd", *case(16, 50, 37, 33, 17))
+    ok &= run("C=256", *case(17, 50, 20, 256, 40))
     if mode == "full":
-        ok &= run("C=1024 L<=256", *case(9, 600, 6, 1024, 256))
-        ok &= run("peaked 8 L<=256", *case(10, 1024, 4, 1024, 256, ragged=False, boost=8.0, Lmin=200))
+        if DEFAULT_FLAGS != _ffi.FLAG_SEQWARP:
+            ok &= run("C=1024 L<=256", *case(9, 600, 6, 1024, 256))
+            ok &= run("peaked 8 L<=256", *case(10, 1024, 4, 1024, 256, ragged=False, boost=8.0, Lmin=200))
+        ok &= run("multi-wave ragged B=9000", *case(18, 40, 9000, 40, 12))
         ok &= run("cfg2 quarter", *case(11, 256, 1024, 157, 32, ragged=False))
         ok &= run("cfg2 ragged", *case(12, 256, 1024, 157, 32, ragged=True))
         ok &= run("cfg5 slice", *case(13, 512, 512, 157, 64, ragged=False))
