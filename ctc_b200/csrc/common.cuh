@@ -78,6 +78,7 @@ int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream
 
 // sequence-per-warp path of the single-label variant (nbctc_seqwarp.cu: one warp per sequence, whole batch in flight)
 bool seqwarp_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
+bool seqwarp_is_wide(int64_t T, int64_t B, int64_t C, int64_t Lmax);  // rows through a shared-memory ring (needs 16-byte alignment)
 size_t seqwarp_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row_lse_in, float* row_lse_out, cudaStream_t stream);
 

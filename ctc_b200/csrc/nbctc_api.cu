@@ -66,7 +66,7 @@ bool want_seqwarp(uint32_t flags, int64_t T, int64_t B, int64_t C, int64_t Lmax)
   if (!seqwarp_supported(T, B, C, Lmax)) return false;
   if (flags & kPathFlags) return (flags & NBCTC_FLAG_SEQWARP) != 0;
   if (env_path()) return env_path() == 3;
-  return B >= 2048;
+  return B >= (seqwarp_is_wide(T, B, C, Lmax) ? 512 : 2048);
 }
 
 int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void* tg, int64_t Lmax,
@@ -90,7 +90,9 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
         float* row_lse_out = nullptr) {
   if (flags & NBCTC_FLAG_NO_GRAD) p.grad = nullptr;
   int rc;
-  const bool use_sw = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_seqwarp(flags, p.T, p.B, p.C, p.Lmax);
+  bool use_sw = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_seqwarp(flags, p.T, p.B, p.C, p.Lmax);
+  // the wide-row variant moves rows with TMA: 16-byte aligned tensors only (else the paths below)
+  if (use_sw && seqwarp_is_wide(p.T, p.B, p.C, p.Lmax) && !fused_pointers_ok(p)) use_sw = false;
   if ((row_lse_in || row_lse_out) && !use_sw) {
     set_error("row_lse needs the sequence-per-warp kernel (single-label variant, C <= 256, Lmax <= 64)");
     return NBCTC_ERR_UNSUPPORTED;
@@ -297,7 +299,11 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   size_t f = 0;
   if (fused_supported(T, B, C, Lmax, binary != 0)) f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
   if (!binary && want_pipeline(flags) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
-  if (!binary && want_seqwarp(flags, T, B, C, Lmax)) return seqwarp_workspace_bytes(T, B, C, Lmax);  // any alignment
+  if (!binary && want_seqwarp(flags, T, B, C, Lmax)) {
+    const size_t sw = seqwarp_workspace_bytes(T, B, C, Lmax);
+    if (!seqwarp_is_wide(T, B, C, Lmax)) return sw;  // any alignment
+    return std::max(sw, f ? ((flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f)) : g);
+  }
   if (f) return (flags & NBCTC_FLAG_ALIGNED16) ? f : std::max(g, f);
   if (binary && tiled_bin_supported(T, B, C, Lmax)) return align_up(g, 256) + tiled_bin_workspace_bytes(T, B, C, Lmax);
   return g;

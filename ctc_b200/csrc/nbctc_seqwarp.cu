@@ -5,9 +5,11 @@
 // Algorithmic HBM bytes per launch: 2*4*T*B*C (logits read once, gradient written once).  The kernel itself moves
 // 3*4*T*B*C (the logits are read again in phase 2) + 4 bytes per row of log-partitions + one 8-byte alpha
 // checkpoint per state and 4 steps, both ways.
+#include <stdlib.h>
+
 #include <algorithm>
 
-#include "seqwarp_kernel.cuh"
+#include "seqwide_kernel.cuh"
 
 namespace nbctc {
 namespace {
@@ -48,16 +50,39 @@ __global__ void __launch_bounds__(kPrepThreads) seqwarp_prep_kernel(const int64_
 
 struct SwPlan {
   bool ok;
+  bool wide;        // seqwide_kernel.cuh (rows through a shared-memory ring) instead of seqwarp_kernel.cuh (registers)
   int NS, EPL, K, Tp;
+  int NV, D;        // wide: float4 chunks per lane, ring slots per warp
+  uint32_t o_gam, o_nxt, o_ring, smem_bytes;
   size_t o_order, o_lse, o_ckx, o_cke, bytes;
 };
 
+constexpr size_t kWideSmemBudget = 31 * 1024;  // per warp-CTA: 7 of them (+1 KB each of driver reserve) share an SM
+
 SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   SwPlan pl{};
-  if (T < 1 || B < 1 || C < 1 || Lmax < 1 || Lmax > 64 || C > 256 || T > (1 << 24) || B > (1 << 24)) return pl;
+  if (T < 1 || B < 1 || C < 1 || Lmax < 1 || T > (1 << 24) || B > (1 << 24) || B * C >= ((int64_t)1 << 26)) return pl;
   if (T * B * C >= ((int64_t)1 << 40)) return pl;
-  pl.NS = Lmax <= 32 ? 1 : 2;
-  pl.EPL = (int)((C + 31) / 32);
+  if (Lmax <= 64 && C <= 256) {
+    pl.NS = Lmax <= 32 ? 1 : 2;
+    pl.EPL = (int)((C + 31) / 32);
+  } else if (Lmax <= 256 && C <= 1024 && C % 4 == 0 && C >= 16) {
+    pl.wide = true;
+    pl.NS = Lmax <= 32 ? 1 : Lmax <= 64 ? 2 : Lmax <= 128 ? 4 : 8;
+    pl.NV = C <= 512 ? 4 : 8;
+    size_t off = 64;  // mbarriers
+    pl.o_gam = (uint32_t)off;
+    off = align_up(off + sizeof(float) * (32 * pl.NS + 4), 16);
+    pl.o_nxt = (uint32_t)off;
+    off = align_up(off + sizeof(unsigned short) * (32 * pl.NS + 4), 128);
+    pl.o_ring = (uint32_t)off;
+    const int64_t d = ((int64_t)kWideSmemBudget - (int64_t)off) / (C * 4);
+    if (d < 5) return pl;  // a tile of 4 rows + one in flight
+    pl.D = (int)std::min<int64_t>(d, 8);
+    pl.smem_bytes = (uint32_t)(off + (size_t)pl.D * C * 4);
+  } else {
+    return pl;
+  }
   pl.K = (int)((T + 3) / 4);
   pl.Tp = pl.K * 4;
   size_t off = 256;
@@ -80,6 +105,7 @@ int g_blocks_per_sm[3] = {0, 0, 0};
 }  // namespace
 
 bool seqwarp_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax) { return make_plan(T, B, C, Lmax).ok; }
+bool seqwarp_is_wide(int64_t T, int64_t B, int64_t C, int64_t Lmax) { return make_plan(T, B, C, Lmax).wide; }
 
 size_t seqwarp_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   const SwPlan pl = make_plan(T, B, C, Lmax);
@@ -102,6 +128,37 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
     NBCTC_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   char* w = static_cast<char*>(ws);
+  if (pl.wide) {
+    if (row_lse_in || row_lse_out) {
+      set_error("row_lse is not available on the wide-row kernel (C > 256 or Lmax > 64)");
+      return NBCTC_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(p.logits) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.grad) & 15) != 0) {
+      set_error("the wide-row kernel needs 16-byte aligned logits / grad_logits");
+      return NBCTC_ERR_UNSUPPORTED;
+    }
+    WideParams W{};
+    W.p = p;
+    W.lse2 = reinterpret_cast<float*>(w + pl.o_lse);
+    W.ckx = reinterpret_cast<double*>(w + pl.o_ckx);
+    W.cke = reinterpret_cast<int*>(w + pl.o_cke);
+    W.K = pl.K;
+    W.Tp = pl.Tp;
+    W.D = pl.D;
+    W.o_gam = pl.o_gam; W.o_nxt = pl.o_nxt; W.o_ring = pl.o_ring; W.smem_bytes = pl.smem_bytes;
+    const int64_t resident = (int64_t)(pl.NS >= 8 ? 7 : 8) * g_sms;
+    int grid;
+    if (p.B <= resident) {
+      grid = (int)p.B;
+    } else {
+      grid = (int)resident;
+      W.ticket = reinterpret_cast<int*>(w);
+      W.order = reinterpret_cast<int*>(w + pl.o_order);
+      seqwarp_prep_kernel<<<1, kPrepThreads, 0, stream>>>(p.in_len, (int)p.B, (int)p.T, const_cast<int*>(W.order), W.ticket);
+      NBCTC_LAUNCH_CHECK();
+    }
+    return pl.NV == 4 ? launch_seqwide_nv<4>(W, pl.NS, grid, stream) : launch_seqwide_nv<8>(W, pl.NS, grid, stream);
+  }
   SwParams P{};
   P.p = p;
   P.lse2 = reinterpret_cast<float*>(w + pl.o_lse);
@@ -111,6 +168,12 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
   P.row_lse_out = row_lse_out;
   P.K = pl.K;
   P.Tp = pl.Tp;
+  static const int pf_mode = [] { const char* v = getenv("NBCTC_SW_PF"); return v ? atoi(v) : 2; }();
+  static const int pf_dist = [] { const char* v = getenv("NBCTC_SW_PFD"); return v ? atoi(v) : 2; }();
+  P.pf_mode = pf_mode;
+  P.pf_dist = std::max(1, pf_dist);
+  static const int pf_near = [] { const char* v = getenv("NBCTC_SW_PFN"); return v ? atoi(v) : 1; }();
+  P.pf_near = std::max(1, pf_near);
   const int per_sm = seqwarp_ctas_per_sm(pl.NS);
   const int64_t resident = (int64_t)per_sm * g_sms;  // CTAs of one warp
   const int64_t need = p.B;

@@ -46,6 +46,9 @@ struct SwParams {
   float* row_lse_out;       // (T,B) or null: row log-partitions handed to the caller
   int K;                // tiles = ceil(T / 4)
   int Tp;
+  int pf_mode;          // bit 0: per-line L2 prefetch pf_dist tiles ahead, bit 1: per-line L1 prefetch one tile ahead,
+  int pf_dist;          // bit 2: TMA bulk L2 prefetch pf_dist tiles ahead
+  int pf_near;          // tiles between the L1 prefetch and the loads
 };
 
 int launch_seqwarp(const SwParams& P, int NS, int EPL, int grid, cudaStream_t stream);
@@ -103,7 +106,8 @@ __device__ __forceinline__ float ldg_f(const float* p) {
 __device__ __forceinline__ void prefetch_l2(const void* a, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
 }
-constexpr int kPfTiles = 2;  // rows are requested into L2 this many tiles ahead of their loads
+__device__ __forceinline__ void pf_line_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+__device__ __forceinline__ void pf_line_l1(const void* a) { asm volatile("prefetch.global.L1 [%0];" ::"l"(a)); }
 
 // New lane scales after a prefix-max scan along the direction mass moves (UP: towards higher lanes, alpha; else
 // towards lower lanes, beta): e_l = max_{k upstream of l}(A_k - DEC dist(k,l)), A_k = absolute exponent of lane k's
@@ -353,13 +357,30 @@ __device__ void Seq<NS, EPL>::run(int b) {
   double fac = lane == 0 ? 0.0 : 1.0;
 
   const int Kf = Tb / kTT;  // full tiles
-  // L2 prefetch: lane i < 4 requests row 4 k' + i of a tile k' = k + kPfTiles (the 16-byte chunks inside the row)
+  // Prefetch.  Bulk mode: lane i < 4 requests row 4 k' + i of the tile k' = k + pf_dist with one TMA L2 prefetch (the
+  // 16-byte chunks inside the row).  Line mode: lane = (row of the tile, 128-byte line of the row); one instruction
+  // requests the whole tile, pf_dist tiles ahead into L2 and / or one tile ahead into L1.
+  const int pfd = P.pf_dist;
+  const bool pf_bulk = (P.pf_mode & 4) && C >= 8, pf_l2 = P.pf_mode & 1, pf_l1 = P.pf_mode & 2;
   const uint32_t pf_bytes = (uint32_t)(((C * 4 - 12) & ~15));
   auto pf_addr = [&](int t) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p.logits + ((int64_t)t * B + b) * C);
     return reinterpret_cast<const void*>((a + 15) & ~(uintptr_t)15);
   };
-  if (!have_lse && C >= 8 && lane < kTT * kPfTiles && lane < Tb) prefetch_l2(pf_addr(lane), pf_bytes);
+  const int LW = min((C * 4 + 127) / 128 + 1, 8);  // lanes per row: lines 0, 128, ... and the row's last element
+  const bool pf_lane = lane < kTT * LW;
+  const int pf_ri = lane / LW, pf_off = min((lane - pf_ri * LW) * 128, C * 4 - 4);
+  const char* const pf_base = reinterpret_cast<const char*>(p.logits + (int64_t)b * C) + pf_off;  // + t * strideT * 4
+  const int64_t strideB = strideT * 4;
+  auto pf_tile = [&](int kk, bool l1) {  // rows of tile kk
+    const char* a = pf_base + (int64_t)(kk * kTT + pf_ri) * strideB;
+    if (l1) pf_line_l1(a); else pf_line_l2(a);
+  };
+  if (!have_lse) {
+    if (pf_bulk && lane < kTT * pfd && lane < Kf * kTT) prefetch_l2(pf_addr(lane), pf_bytes);
+    if (pf_l2 && pf_lane)
+      for (int kk = 0; kk < min(pfd, Kf); ++kk) pf_tile(kk, false);
+  }
   const float* rq = row0;  // first row of the tile
   for (int k = 0; k < Kf; ++k) {
     float xg[kTT][NS];
@@ -381,10 +402,11 @@ __device__ void Seq<NS, EPL>::run(int b) {
         for (int j = 0; j < NS; ++j) xg[i][j] = ldg_f(rq + goff[j]);
         rq += strideT;
       }
-      if (C >= 8 && lane < kTT) {
-        const int t = (k + kPfTiles) * kTT + lane;
-        if (t < Tb) prefetch_l2(pf_addr(t), pf_bytes);
+      if (k + pfd < Kf) {
+        if (pf_bulk && lane < kTT) prefetch_l2(pf_addr((k + pfd) * kTT + lane), pf_bytes);
+        if (pf_l2 && pf_lane) pf_tile(k + pfd, false);
       }
+      if (pf_l1 && pf_lane && k + P.pf_near < Kf) pf_tile(k + P.pf_near, true);
       float nm[kTT], s[kTT];
 #pragma unroll
       for (int i = 0; i < kTT; ++i) nm[i] = -kL2E * row_max(xr[i]);
@@ -561,9 +583,20 @@ __device__ void Seq<NS, EPL>::run(int b) {
     const float* rl = row0 + (int64_t)(Kf * kTT - 1) * strideT;  // next row to load, walking down
     int since = 0;                                              // tiles since the last beta rescale
     for (int k = Kf - 1; k >= 0; --k) {
-      if (C >= 8 && lane < kTT) {
-        const int t = (k - kPfTiles) * kTT + lane;
-        if (t >= 0) prefetch_l2(pf_addr(t), pf_bytes);
+      if (k - pfd >= 0) {
+        if (pf_bulk && lane < kTT) prefetch_l2(pf_addr((k - pfd) * kTT + lane), pf_bytes);
+        if (pf_l2 && pf_lane) pf_tile(k - pfd, false);
+      }
+      if (pf_l1 && pf_lane && k >= P.pf_near) pf_tile(k - P.pf_near, true);
+      if (k > 0) {
+        // the tile's checkpoint, lane scales and log-partitions one tile ahead
+        if (pf_l1 && lane >= 28) {
+          const char* a = lane == 28 ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad)
+                        : lane == 29 ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad) + 128 * NS
+                        : lane == 30 ? reinterpret_cast<const char*>(cke - lane + ((k - 1) >> 1) * 32)
+                                     : reinterpret_cast<const char*>(lse_ws + (k - 1) * kTT);
+          pf_line_l1(a);
+        }
       }
       float xg[kTT][NS];
       {

@@ -88,9 +88,11 @@ def main():
     ok &= run("C=33 odd", *case(16, 50, 37, 33, 17))
     ok &= run("C=256", *case(17, 50, 20, 256, 40))
     if mode == "full":
-        if DEFAULT_FLAGS != _ffi.FLAG_SEQWARP:
-            ok &= run("C=1024 L<=256", *case(9, 600, 6, 1024, 256))
-            ok &= run("peaked 8 L<=256", *case(10, 1024, 4, 1024, 256, ragged=False, boost=8.0, Lmin=200))
+        ok &= run("C=1024 L<=256", *case(9, 600, 6, 1024, 256))
+        ok &= run("peaked 8 L<=256", *case(10, 1024, 4, 1024, 256, ragged=False, boost=8.0, Lmin=200))
+        ok &= run("C=512 L<=100 dup", *case(19, 77, 9, 512, 100, dup=True))
+        ok &= run("C=160 L<=128", *case(20, 300, 7, 160, 128))
+        ok &= run("wide multi-wave B=1500", *case(21, 24, 1500, 64, 70))
         ok &= run("multi-wave ragged B=9000", *case(18, 40, 9000, 40, 12))
         ok &= run("cfg2 quarter", *case(11, 256, 1024, 157, 32, ragged=False))
         ok &= run("cfg2 ragged", *case(12, 256, 1024, 157, 32, ragged=True))
