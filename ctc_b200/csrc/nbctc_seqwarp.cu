@@ -77,8 +77,8 @@ SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
     off = align_up(off + sizeof(unsigned short) * (32 * pl.NS + 4), 128);
     pl.o_ring = (uint32_t)off;
     const int64_t d = ((int64_t)kWideSmemBudget - (int64_t)off) / (C * 4);
-    if (d < 5) return pl;  // a tile of 4 rows + one in flight
-    pl.D = (int)std::min<int64_t>(d, 8);
+    if (d < 7) return pl;  // a tile of 4 rows + the first 3 of the next one
+    pl.D = 7;
     pl.smem_bytes = (uint32_t)(off + (size_t)pl.D * C * 4);
   } else {
     return pl;

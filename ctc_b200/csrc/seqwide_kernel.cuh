@@ -10,7 +10,9 @@
 //   * a lane reads the row as float4 (conflict-free), the per-state label gathers come from the same slot;
 //   * phase 2 turns the slot into the gradient row IN PLACE (w softmax, then the first state of every label overwrites
 //     its class with the corrected value) and lane 0 sends it to the gradient tensor with ONE bulk store; the slot is
-//     reloaded one step later, when that store has read it (cp.async.bulk.wait_group.read).
+//     refilled one step later, when that store has read it (cp.async.bulk.wait_group.read).  Seven slots: the tile of 4
+//     rows being worked on + the first 3 rows of the next tile, requested lowest row first (the order the alpha replay
+//     consumes them).
 // Template parameters: NS states per lane (Lmax <= 32 NS), NV float4 chunks per lane (C <= 128 NV).
 #pragma once
 
@@ -293,22 +295,10 @@ __device__ void Wide<NS, NV>::run(int b) {
   int eb = 0;
   double facb = lane == 31 ? 0.0 : 1.0;
   float* const gseq0 = p.grad + (int64_t)b * C;
-  // descending row index d = Tb-1-t lives in slot d % D
-  int next_d = min(D, Tb);
-  for (int d = 0; d < next_d; ++d) issue_load(d, seq0 + (int64_t)(Tb - 1 - d) * strideT);
-  int prev_slot = -1;
-  const int Kb = (Tb + kTT - 1) / kTT;
-  int since = 0;
-  for (int k = Kb - 1; k >= 0; --k) {
-    const int t0 = k * kTT;
-    const int nv = min(kTT, Tb - t0);
-    int slot_i[kTT];
-#pragma unroll
-    for (int i = kTT - 1; i >= 0; --i) {
-      slot_i[i] = (Tb - 1 - (t0 + i)) % D;
-      if (i < nv) wait_load(slot_i[i]);
-    }
-    double xa[NS];
+  const int Kf = Tb / kTT, nrem = Tb - Kf * kTT;
+
+  // alpha state, lane scale in front of tile k; then the scale factors of gamma (seqwarp_kernel.cuh)
+  auto load_ck = [&](int k, double (&xa)[NS], double& gb, double& faca) {
     int ea = 0;
     if (k == 0) {
 #pragma unroll
@@ -333,79 +323,125 @@ __device__ void Wide<NS, NV>::run(int b) {
     }
     const int H = ea + eb - Ez;
     const int Ha = max(min(H, 0), -1000);
-    const double ga = pow2z(Ha), gb = pow2z(H - Ha) * zinv;
+    const double ga = pow2z(Ha);
+    gb = pow2z(H - Ha) * zinv;
     const int es = ea - Ha;
     const int eu = __shfl_up_sync(kFull, es, 1);
-    const double faca = lane == 0 ? 0.0 : pow2z(eu - es);
-    float nl[kTT];
-    if (nv == kTT) {
-      const float4 l4 = *reinterpret_cast<const float4*>(lse_ws + t0);
-      nl[0] = -l4.x; nl[1] = -l4.y; nl[2] = -l4.z; nl[3] = -l4.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < kTT; ++i) nl[i] = i < nv ? -lse_ws[t0 + i] : 0.f;
-    }
-    float pe[kTT][NS];
-    double a[kTT][NS];
+    faca = lane == 0 ? 0.0 : pow2z(eu - es);
 #pragma unroll
     for (int j = 0; j < NS; ++j) xa[j] *= ga;
+  };
+  // one backward step on the row in `slot` (time t): beta, gamma, the slot becomes the gradient row in place and
+  // leaves with one bulk store
+  auto grad_step = [&](int slot, int t, const double (&a)[NS], const float (&pe)[NS], float nl, double gb) {
+    double bt[NS];
+    beta_step<NS>(u, bt, pe, facb);
+    float g[NS];
 #pragma unroll
-    for (int i = 0; i < kTT; ++i) {
-      if (i < nv) {
-        emissions(slot_i[i], nl[i], lab, actm, pe[i]);
+    for (int j = 0; j < NS; ++j) g[j] = (float)(a[j] * fmin(bt[j] * gb, 1e300));
+    const float nlw = nl + lw;
+    float4* r4 = row4(slot);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int c4 = lane + 32 * q;
+      if (c4 < C4) {
+        float4 v = r4[c4];
+        v.x = ex2f(fmaf(v.x, kL2E, nlw));
+        v.y = ex2f(fmaf(v.y, kL2E, nlw));
+        v.z = ex2f(fmaf(v.z, kL2E, nlw));
+        v.w = ex2f(fmaf(v.w, kL2E, nlw));
+        r4[c4] = v;
+      }
+    }
+    combine(g, nx1, R);  // (its barrier also orders the row writes before the corrected entries)
+    float* rf = rowf(slot);
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      if ((leadm >> j) & 1u) rf[lab[j]] = fmaf(w, pe[j], -g[j]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g_hint(reinterpret_cast<uint64_t>(gseq0 + (int64_t)t * strideT), smem_u32(r4), (uint32_t)RB, pol);
+      bulk_commit();
+    }
+  };
+
+  if (nrem > 0) {  // the sequence's last steps, one at a time through slot 0
+    const int k = Kf;
+    double xa0[NS], gb, faca;
+    load_ck(k, xa0, gb, faca);
+    for (int i = nrem - 1; i >= 0; --i) {
+      const int t = k * kTT + i;
+      issue_load(0, seq0 + (int64_t)t * strideT);
+      double xa[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xa[j] = xa0[j];
+      float pr[NS], nl = 0.f;
+      for (int ii = 0; ii <= i; ++ii) {  // replay up to step i (label entries straight from global memory)
+        nl = -lse_ws[k * kTT + ii];
+        const float* rp = seq0 + (int64_t)(k * kTT + ii) * strideT;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) pr[j] = (actm >> j) & 1u ? fmaxf(ex2f(fmaf(__ldg(rp + lab[j]), kL2E, nl)), kPFloor) : 0.f;
+        alpha_step<NS>(xa, pr, faca);
+      }
+      wait_load(0);
+      grad_step(0, t, xa, pr, nl, gb);
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
+    }
+    lane_rescale<NS, false>(u, eb, facb, lane);
+  }
+
+  if (Kf > 0) {
+    // Seven slots: the four rows of the tile being worked on and the first three of the next tile down.  Rows are
+    // requested in the order the alpha replay needs them (a tile's lowest row first), so the row a tile waits for
+    // first has been in flight for a whole tile.  A slot is refilled one step after its bulk store was issued.
+    int cur[kTT] = {0, 1, 2, 3};  // slot of row t0 + i
+    int nx3[3] = {4, 5, 6};       // slot of row t0 - 4 + r
+    {
+      const int t0 = (Kf - 1) * kTT;
+#pragma unroll
+      for (int i = 0; i < kTT; ++i) issue_load(cur[i], seq0 + (int64_t)(t0 + i) * strideT);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (t0 - kTT + r >= 0) issue_load(nx3[r], seq0 + (int64_t)(t0 - kTT + r) * strideT);
+    }
+    int pend_slot = -1, pend_t = -1;  // slot whose store was issued in the previous step, and the row it takes next
+    int since = 0;
+    for (int k = Kf - 1; k >= 0; --k) {
+      const int t0 = k * kTT;
+      double xa[NS], gb, faca;
+      load_ck(k, xa, gb, faca);
+      const float4 l4 = *reinterpret_cast<const float4*>(lse_ws + t0);
+      const float nl[kTT] = {-l4.x, -l4.y, -l4.z, -l4.w};
+      float pe[kTT][NS];
+      double a[kTT][NS];
+#pragma unroll
+      for (int i = 0; i < kTT; ++i) {
+        wait_load(cur[i]);
+        emissions(cur[i], nl[i], lab, actm, pe[i]);
         alpha_step<NS>(xa, pe[i], faca);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) a[i][j] = xa[j];
       }
 #pragma unroll
-      for (int j = 0; j < NS; ++j) a[i][j] = xa[j];
-    }
-#pragma unroll
-    for (int i = kTT - 1; i >= 0; --i) {
-      if (i < nv) {
-        const int slot = slot_i[i];
-        double bt[NS];
-        beta_step<NS>(u, bt, pe[i], facb);
-        float g[NS];
-#pragma unroll
-        for (int j = 0; j < NS; ++j) g[j] = (float)(a[i][j] * fmin(bt[j] * gb, 1e300));
-        // the slot becomes w softmax(x) in place
-        const float nlw = nl[i] + lw;
-        float4* r4 = row4(slot);
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          const int c4 = lane + 32 * q;
-          if (c4 < C4) {
-            float4 v = r4[c4];
-            v.x = ex2f(fmaf(v.x, kL2E, nlw));
-            v.y = ex2f(fmaf(v.y, kL2E, nlw));
-            v.z = ex2f(fmaf(v.z, kL2E, nlw));
-            v.w = ex2f(fmaf(v.w, kL2E, nlw));
-            r4[c4] = v;
-          }
+      for (int i = kTT - 1; i >= 0; --i) {
+        grad_step(cur[i], t0 + i, a[i], pe[i], nl[i], gb);
+        if (pend_slot >= 0 && pend_t >= 0) {
+          if (lane == 0) bulk_wait_read<1>();  // the previous step's store has read its slot
+          issue_load(pend_slot, seq0 + (int64_t)pend_t * strideT);
         }
-        combine(g, nx1, R);  // (its barrier also orders the row writes before the corrected entries)
-        float* rf = rowf(slot);
-#pragma unroll
-        for (int j = 0; j < NS; ++j)
-          if ((leadm >> j) & 1u) rf[lab[j]] = fmaf(w, pe[i][j], -g[j]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_s2g_hint(reinterpret_cast<uint64_t>(gseq0 + (int64_t)(t0 + i) * strideT), smem_u32(r4), (uint32_t)RB, pol);
-          bulk_commit();
-          if (prev_slot >= 0 && next_d < Tb) {
-            bulk_wait_read<1>();  // the previous row's store has read its slot
-          }
-        }
-        if (prev_slot >= 0 && next_d < Tb) {
-          issue_load(prev_slot, seq0 + (int64_t)(Tb - 1 - next_d) * strideT);
-          ++next_d;
-        }
-        prev_slot = slot;
+        pend_slot = cur[i];
+        pend_t = i == kTT - 1 ? t0 - 1 : t0 - 2 * kTT + (2 - i);  // (k-1, row 3), then (k-2, rows 0, 1, 2)
       }
-    }
-    if (++since == 2 || nv < kTT) {
-      since = 0;
-      lane_rescale<NS, false>(u, eb, facb, lane);
+      // the next tile down: its rows 0..2 are in nx3, row 3 takes the slot of this tile's row 3
+      const int c0 = cur[0], c1 = cur[1], c2 = cur[2];
+      cur[0] = nx3[0]; cur[1] = nx3[1]; cur[2] = nx3[2];
+      nx3[0] = c2; nx3[1] = c1; nx3[2] = c0;
+      if (++since == 2) {
+        since = 0;
+        lane_rescale<NS, false>(u, eb, facb, lane);
+      }
     }
   }
   if (lane == 0) bulk_wait_all();  // the ring is reused by the next sequence; the stores must have left shared memory
