@@ -169,9 +169,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
   P.K = pl.K;
   P.Tp = pl.Tp;
   static const int pf_mode = [] { const char* v = getenv("NBCTC_SW_PF"); return v ? atoi(v) : 2; }();
-  static const int pf_dist = [] { const char* v = getenv("NBCTC_SW_PFD"); return v ? atoi(v) : 2; }();
   P.pf_mode = pf_mode;
-  P.pf_dist = std::max(1, pf_dist);
   static const int pf_near = [] { const char* v = getenv("NBCTC_SW_PFN"); return v ? atoi(v) : 1; }();
   P.pf_near = std::max(1, pf_near);
   const int per_sm = seqwarp_ctas_per_sm(pl.NS);

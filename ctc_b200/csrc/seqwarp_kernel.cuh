@@ -46,8 +46,7 @@ struct SwParams {
   float* row_lse_out;       // (T,B) or null: row log-partitions handed to the caller
   int K;                // tiles = ceil(T / 4)
   int Tp;
-  int pf_mode;          // bit 0: per-line L2 prefetch pf_dist tiles ahead, bit 1: per-line L1 prefetch one tile ahead,
-  int pf_dist;          // bit 2: TMA bulk L2 prefetch pf_dist tiles ahead
+  int pf_mode;          // bit 1: per-line L1 prefetch of the next tile's rows, checkpoint and log-partitions
   int pf_near;          // tiles between the L1 prefetch and the loads
 };
 
@@ -95,6 +94,11 @@ __device__ __forceinline__ double pow2z(int e) {
   e = min(e, 1023);
   return e < -1022 ? 0.0 : __hiloint2double((1023 + e) << 20, 0);
 }
+// min(v, 2^996) on the bit pattern: one integer instruction where fmin() on doubles takes three; inf and NaN (an
+// overflowed beta factor next to an alpha that flushed to zero) come back as 2^996 too, negative values pass
+__device__ __forceinline__ double clamp_big(double v) {
+  return __hiloint2double(min(__double2hiint(v), 0x7E300000), __double2loint(v));
+}
 // volatile: the order of the row requests relative to each other is ours (the compiler would hoist every load of a
 // tile to its top and spill the rows)
 __device__ __forceinline__ float ldg_f(const float* p) {
@@ -102,11 +106,6 @@ __device__ __forceinline__ float ldg_f(const float* p) {
   asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-// TMA prefetch of [a, a + bytes) into L2 (both 16-byte multiples): costs no register and no shared memory
-__device__ __forceinline__ void prefetch_l2(const void* a, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pf_line_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 __device__ __forceinline__ void pf_line_l1(const void* a) { asm volatile("prefetch.global.L1 [%0];" ::"l"(a)); }
 
 // New lane scales after a prefix-max scan along the direction mass moves (UP: towards higher lanes, alpha; else
@@ -357,30 +356,15 @@ __device__ void Seq<NS, EPL>::run(int b) {
   double fac = lane == 0 ? 0.0 : 1.0;
 
   const int Kf = Tb / kTT;  // full tiles
-  // Prefetch.  Bulk mode: lane i < 4 requests row 4 k' + i of the tile k' = k + pf_dist with one TMA L2 prefetch (the
-  // 16-byte chunks inside the row).  Line mode: lane = (row of the tile, 128-byte line of the row); one instruction
-  // requests the whole tile, pf_dist tiles ahead into L2 and / or one tile ahead into L1.
-  const int pfd = P.pf_dist;
-  const bool pf_bulk = (P.pf_mode & 4) && C >= 8, pf_l2 = P.pf_mode & 1, pf_l1 = P.pf_mode & 2;
-  const uint32_t pf_bytes = (uint32_t)(((C * 4 - 12) & ~15));
-  auto pf_addr = [&](int t) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p.logits + ((int64_t)t * B + b) * C);
-    return reinterpret_cast<const void*>((a + 15) & ~(uintptr_t)15);
-  };
+  // L1 prefetch: lane = (row of a tile, 128-byte line of the row); ONE instruction requests a whole tile, pf_near tiles
+  // ahead of its loads (measured: L2 prefetches further ahead, per line or as TMA bulk prefetch, only cost time)
+  const bool pf_l1 = P.pf_mode & 2;
   const int LW = min((C * 4 + 127) / 128 + 1, 8);  // lanes per row: lines 0, 128, ... and the row's last element
   const bool pf_lane = lane < kTT * LW;
   const int pf_ri = lane / LW, pf_off = min((lane - pf_ri * LW) * 128, C * 4 - 4);
   const char* const pf_base = reinterpret_cast<const char*>(p.logits + (int64_t)b * C) + pf_off;  // + t * strideT * 4
   const int64_t strideB = strideT * 4;
-  auto pf_tile = [&](int kk, bool l1) {  // rows of tile kk
-    const char* a = pf_base + (int64_t)(kk * kTT + pf_ri) * strideB;
-    if (l1) pf_line_l1(a); else pf_line_l2(a);
-  };
-  if (!have_lse) {
-    if (pf_bulk && lane < kTT * pfd && lane < Kf * kTT) prefetch_l2(pf_addr(lane), pf_bytes);
-    if (pf_l2 && pf_lane)
-      for (int kk = 0; kk < min(pfd, Kf); ++kk) pf_tile(kk, false);
-  }
+  auto pf_tile = [&](int kk) { pf_line_l1(pf_base + (int64_t)(kk * kTT + pf_ri) * strideB); };
   const float* rq = row0;  // first row of the tile
   for (int k = 0; k < Kf; ++k) {
     float xg[kTT][NS];
@@ -402,11 +386,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
         for (int j = 0; j < NS; ++j) xg[i][j] = ldg_f(rq + goff[j]);
         rq += strideT;
       }
-      if (k + pfd < Kf) {
-        if (pf_bulk && lane < kTT) prefetch_l2(pf_addr((k + pfd) * kTT + lane), pf_bytes);
-        if (pf_l2 && pf_lane) pf_tile(k + pfd, false);
-      }
-      if (pf_l1 && pf_lane && k + P.pf_near < Kf) pf_tile(k + P.pf_near, true);
+      if (pf_l1 && pf_lane && k + P.pf_near < Kf) pf_tile(k + P.pf_near);
       float nm[kTT], s[kTT];
 #pragma unroll
       for (int i = 0; i < kTT; ++i) nm[i] = -kL2E * row_max(xr[i]);
@@ -514,7 +494,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
     beta_step<NS>(u, bt, pe, facb);
     float g[NS];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) g[j] = (float)(a[j] * fmin(bt[j] * gb, 1e300));
+    for (int j = 0; j < NS; ++j) g[j] = (float)(a[j] * clamp_big(bt[j] * gb));
     const float nlw = nl + lw;  // the softmax row, scaled by the sequence weight
     float r[EPL];
 #pragma unroll
@@ -583,11 +563,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
     const float* rl = row0 + (int64_t)(Kf * kTT - 1) * strideT;  // next row to load, walking down
     int since = 0;                                              // tiles since the last beta rescale
     for (int k = Kf - 1; k >= 0; --k) {
-      if (k - pfd >= 0) {
-        if (pf_bulk && lane < kTT) prefetch_l2(pf_addr((k - pfd) * kTT + lane), pf_bytes);
-        if (pf_l2 && pf_lane) pf_tile(k - pfd, false);
-      }
-      if (pf_l1 && pf_lane && k >= P.pf_near) pf_tile(k - P.pf_near, true);
+      if (pf_l1 && pf_lane && k >= P.pf_near) pf_tile(k - P.pf_near);
       if (k > 0) {
         // the tile's checkpoint, lane scales and log-partitions one tile ahead
         if (pf_l1 && lane >= 28) {

@@ -54,7 +54,7 @@ using stream::smem_u32;
 
 constexpr int kMaxD = 8;
 
-template <int NS, int NV>
+template <int NS, int NV, bool FULL>
 struct Wide {
   static constexpr int Lpad = 32 * NS;
   const WideParams& P;
@@ -96,7 +96,7 @@ struct Wide {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
-      v[i] = c4 < C4 ? r[c4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      v[i] = (FULL || c4 < C4) ? r[c4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
   }
   __device__ __forceinline__ void zero_rows(int b, int t0, int t1) const {
@@ -144,8 +144,8 @@ struct Wide {
   __device__ void run(int b);
 };
 
-template <int NS, int NV>
-__device__ void Wide<NS, NV>::run(int b) {
+template <int NS, int NV, bool FULL>
+__device__ void Wide<NS, NV, FULL>::run(int b) {
   const Problem& p = P.p;
   const int T = (int)p.T, B = (int)p.B;
   const int64_t Tb64 = p.in_len[b], Lb64 = p.tgt_len[b];
@@ -338,13 +338,13 @@ __device__ void Wide<NS, NV>::run(int b) {
     beta_step<NS>(u, bt, pe, facb);
     float g[NS];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) g[j] = (float)(a[j] * fmin(bt[j] * gb, 1e300));
+    for (int j = 0; j < NS; ++j) g[j] = (float)(a[j] * clamp_big(bt[j] * gb));
     const float nlw = nl + lw;
     float4* r4 = row4(slot);
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
       const int c4 = lane + 32 * q;
-      if (c4 < C4) {
+      if (FULL || c4 < C4) {
         float4 v = r4[c4];
         v.x = ex2f(fmaf(v.x, kL2E, nlw));
         v.y = ex2f(fmaf(v.y, kL2E, nlw));
@@ -412,6 +412,12 @@ __device__ void Wide<NS, NV>::run(int b) {
       const int t0 = k * kTT;
       double xa[NS], gb, faca;
       load_ck(k, xa, gb, faca);
+      if (k > 0) {  // the next tile's checkpoint (lanes 0 .. 2 NS - 1: its 128-byte lines), lane scales and log-partitions
+        const char* a = lane < 2 * NS ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad) + 128 * lane
+                      : lane == 2 * NS ? reinterpret_cast<const char*>(cke - lane + ((k - 1) >> 1) * 32)
+                                       : reinterpret_cast<const char*>(lse_ws + (k - 1) * kTT);
+        if (lane <= 2 * NS + 1) pf_line_l1(a);
+      }
       const float4 l4 = *reinterpret_cast<const float4*>(lse_ws + t0);
       const float nl[kTT] = {-l4.x, -l4.y, -l4.z, -l4.w};
       float pe[kTT][NS];
@@ -449,11 +455,11 @@ __device__ void Wide<NS, NV>::run(int b) {
   if (Tb < T) zero_rows(b, Tb, T);
 }
 
-template <int NS, int NV>
+template <int NS, int NV, bool FULL>
 __global__ void __launch_bounds__(32, NS >= 8 ? 7 : 8) seqwide_kernel(const __grid_constant__ WideParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x;
-  Wide<NS, NV> wd(P, lane, smem);
+  Wide<NS, NV, FULL> wd(P, lane, smem);
   if (lane == 0) {
     for (int i = 0; i < P.D; ++i) mbar_init(&wd.bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -472,16 +478,21 @@ __global__ void __launch_bounds__(32, NS >= 8 ? 7 : 8) seqwide_kernel(const __gr
   }
 }
 
-template <int NS, int NV>
-int launch_wide_one(const WideParams& P, int grid, cudaStream_t stream) {
+template <int NS, int NV, bool FULL>
+int launch_wide_full(const WideParams& P, int grid, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(seqwide_kernel<NS, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 31 * 1024));
+    NBCTC_CUDA_CHECK(cudaFuncSetAttribute(seqwide_kernel<NS, NV, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 31 * 1024));
     attr_done = true;
   }
-  seqwide_kernel<NS, NV><<<grid, 32, P.smem_bytes, stream>>>(P);
+  seqwide_kernel<NS, NV, FULL><<<grid, 32, P.smem_bytes, stream>>>(P);
   NBCTC_LAUNCH_CHECK();
   return NBCTC_OK;
+}
+template <int NS, int NV>
+int launch_wide_one(const WideParams& P, int grid, cudaStream_t stream) {
+  // rows that fill every lane's chunks (C = 128 NV) run without the per-chunk bounds predicates
+  return P.p.C == 128 * NV ? launch_wide_full<NS, NV, true>(P, grid, stream) : launch_wide_full<NS, NV, false>(P, grid, stream);
 }
 
 }  // namespace swd
