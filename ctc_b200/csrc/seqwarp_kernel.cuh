@@ -338,6 +338,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
   }
 
   const bool want_grad = p.grad != nullptr && w != 0.f;
+  const bool ck_lane = act[0];  // only the lanes that hold states take part in the checkpoint traffic
   const bool have_lse = P.row_lse_in != nullptr;
   const float* const row0 = p.logits + (int64_t)b * C + lane;  // row t = 0, this lane's first class
   int goff[NS];                                                 // label's class relative to the lane's first class
@@ -407,9 +408,9 @@ __device__ void Seq<NS, EPL>::run(int b) {
     if (k > 0) {
       if ((k & 1) == 0) {
         lane_rescale<NS, true>(x, e, fac, lane);
-        if (want_grad) cke[(k >> 1) * 32] = e;
+        if (want_grad && ck_lane) cke[(k >> 1) * 32] = e;
       }
-      if (want_grad) {
+      if (want_grad && ck_lane) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) ckx[(int64_t)k * Lpad + j] = x[j];
       }
@@ -424,9 +425,9 @@ __device__ void Seq<NS, EPL>::run(int b) {
     if (k > 0) {
       if ((k & 1) == 0) {
         lane_rescale<NS, true>(x, e, fac, lane);
-        if (want_grad) cke[(k >> 1) * 32] = e;
+        if (want_grad && ck_lane) cke[(k >> 1) * 32] = e;
       }
-      if (want_grad) {
+      if (want_grad && ck_lane) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) ckx[(int64_t)k * Lpad + j] = x[j];
       }
@@ -513,20 +514,20 @@ __device__ void Seq<NS, EPL>::run(int b) {
       for (int j = 0; j < NS; ++j) xa[j] = ((lane * NS + j) & 1) ? -1.0 : 1.0;
     } else {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) xa[j] = ckx[(int64_t)k * Lpad + j];
-      if (k >= 2) ea = cke[(k >> 1) * 32];
+      for (int j = 0; j < NS; ++j) xa[j] = ck_lane ? ckx[(int64_t)k * Lpad + j] : 0.0;
+      if (k >= 2 && ck_lane) ea = cke[(k >> 1) * 32];
     }
   };
-  // gamma_t(s) = alpha beta / Z: the three power-of-two scales split over two exact factors.  ga = 2^Ha <= 1 goes into
-  // the replayed alpha (whose lane scale thereby becomes ea - Ha: the neighbour factor follows), gb into beta.
+  // gamma_t(s) = alpha beta / Z: the three power-of-two scales split over two exact factors.  ga = 2^Ha <= 1 multiplies
+  // the replayed alpha (after the recursion: folded into the recursion it would enter the neighbour factor, which for
+  // lanes whose Ha differ by ~1000 leaves the float64 range), gb = 2^(H-Ha) / Z multiplies beta.
   auto gscales = [&](int ea, double& ga, double& gb, double& faca) {
     const int H = ea + eb - Ez;
     const int Ha = max(min(H, 0), -1000);
     ga = pow2z(Ha);
     gb = pow2z(H - Ha) * zinv;
-    const int es = ea - Ha;
-    const int eu = __shfl_up_sync(kFull, es, 1);
-    faca = lane == 0 ? 0.0 : pow2z(eu - es);
+    const int eu = __shfl_up_sync(kFull, ea, 1);
+    faca = lane == 0 ? 0.0 : pow2z(eu - ea);
   };
 
   if (nrem > 0) {  // the sequence's last steps, one at a time
@@ -535,8 +536,6 @@ __device__ void Seq<NS, EPL>::run(int b) {
     int ea;
     load_ck(k, xa0, ea);
     gscales(ea, ga, gb, faca);
-#pragma unroll
-    for (int j = 0; j < NS; ++j) xa0[j] *= ga;
     for (int i = nrem - 1; i >= 0; --i) {
       double xa[NS];
 #pragma unroll
@@ -553,6 +552,8 @@ __device__ void Seq<NS, EPL>::run(int b) {
       rp -= strideT;
       float r0[EPL];
       load_row(rp, r0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xa[j] *= ga;
       grad_step(xa, pr, nl, gb, r0, const_cast<float*>(rp) + gdelta);
     }
     lane_rescale<NS, false>(u, eb, facb, lane);
@@ -597,12 +598,10 @@ __device__ void Seq<NS, EPL>::run(int b) {
 #pragma unroll
       for (int i = 0; i < kTT; ++i) emissions(xg[i], nl[i], act, pe[i]);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) xa[j] *= ga;
-#pragma unroll
       for (int i = 0; i < kTT; ++i) {
         alpha_step<NS>(xa, pe[i], faca);
 #pragma unroll
-        for (int j = 0; j < NS; ++j) a[i][j] = xa[j];
+        for (int j = 0; j < NS; ++j) a[i][j] = xa[j] * ga;
       }
       float* gr = const_cast<float*>(rl) + gdelta;  // gradient row of the tile's last step
 #pragma unroll

@@ -298,7 +298,7 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
   const int Kf = Tb / kTT, nrem = Tb - Kf * kTT;
 
   // alpha state, lane scale in front of tile k; then the scale factors of gamma (seqwarp_kernel.cuh)
-  auto load_ck = [&](int k, double (&xa)[NS], double& gb, double& faca) {
+  auto load_ck = [&](int k, double (&xa)[NS], double& ga, double& gb, double& faca) {
     int ea = 0;
     if (k == 0) {
 #pragma unroll
@@ -323,13 +323,10 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
     }
     const int H = ea + eb - Ez;
     const int Ha = max(min(H, 0), -1000);
-    const double ga = pow2z(Ha);
+    ga = pow2z(Ha);  // applied to the replayed alpha AFTER the recursion (seqwarp_kernel.cuh: gscales)
     gb = pow2z(H - Ha) * zinv;
-    const int es = ea - Ha;
-    const int eu = __shfl_up_sync(kFull, es, 1);
-    faca = lane == 0 ? 0.0 : pow2z(eu - es);
-#pragma unroll
-    for (int j = 0; j < NS; ++j) xa[j] *= ga;
+    const int eu = __shfl_up_sync(kFull, ea, 1);
+    faca = lane == 0 ? 0.0 : pow2z(eu - ea);
   };
   // one backward step on the row in `slot` (time t): beta, gamma, the slot becomes the gradient row in place and
   // leaves with one bulk store
@@ -368,8 +365,8 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
 
   if (nrem > 0) {  // the sequence's last steps, one at a time through slot 0
     const int k = Kf;
-    double xa0[NS], gb, faca;
-    load_ck(k, xa0, gb, faca);
+    double xa0[NS], ga, gb, faca;
+    load_ck(k, xa0, ga, gb, faca);
     for (int i = nrem - 1; i >= 0; --i) {
       const int t = k * kTT + i;
       issue_load(0, seq0 + (int64_t)t * strideT);
@@ -385,6 +382,8 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
         alpha_step<NS>(xa, pr, faca);
       }
       wait_load(0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xa[j] *= ga;
       grad_step(0, t, xa, pr, nl, gb);
       if (lane == 0) bulk_wait_all();
       __syncwarp();
@@ -410,8 +409,8 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
     int since = 0;
     for (int k = Kf - 1; k >= 0; --k) {
       const int t0 = k * kTT;
-      double xa[NS], gb, faca;
-      load_ck(k, xa, gb, faca);
+      double xa[NS], ga, gb, faca;
+      load_ck(k, xa, ga, gb, faca);
       if (k > 0) {  // the next tile's checkpoint (lanes 0 .. 2 NS - 1: its 128-byte lines), lane scales and log-partitions
         const char* a = lane < 2 * NS ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad) + 128 * lane
                       : lane == 2 * NS ? reinterpret_cast<const char*>(cke - lane + ((k - 1) >> 1) * 32)
@@ -428,7 +427,7 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
         emissions(cur[i], nl[i], lab, actm, pe[i]);
         alpha_step<NS>(xa, pe[i], faca);
 #pragma unroll
-        for (int j = 0; j < NS; ++j) a[i][j] = xa[j];
+        for (int j = 0; j < NS; ++j) a[i][j] = xa[j] * ga;
       }
 #pragma unroll
       for (int i = kTT - 1; i >= 0; --i) {

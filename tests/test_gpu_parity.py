@@ -81,7 +81,7 @@ CTC_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("flags", [0, 1, 16], ids=["default", "generic", "pipeline"])
+@pytest.mark.parametrize("flags", [0, 1, 16, 32], ids=["default", "generic", "pipeline", "seqwarp"])
 @pytest.mark.parametrize("shape", CTC_SHAPES, ids=lambda s: "T%d_B%d_C%d_L%d_%d%d" % s)
 def test_ctc_random_vs_oracle(nb, shape, flags):
     T, B, C, L, ragged, dup = shape
