@@ -168,11 +168,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
   P.row_lse_out = row_lse_out;
   P.K = pl.K;
   P.Tp = pl.Tp;
-  static const int pf_mode = [] { const char* v = getenv("NBCTC_SW_PF"); return v ? atoi(v) : 2; }();
-  P.pf_mode = pf_mode;
-  static const int pf_near = [] { const char* v = getenv("NBCTC_SW_PFN"); return v ? atoi(v) : 1; }();
-  P.pf_near = std::max(1, pf_near);
-  const int per_sm = seqwarp_ctas_per_sm(pl.NS);
+  const int per_sm = seqwarp_ctas_per_sm(pl.NS, pl.EPL);
   const int64_t resident = (int64_t)per_sm * g_sms;  // CTAs of one warp
   const int64_t need = p.B;
   int grid;
@@ -202,6 +198,24 @@ int launch_seqwarp(const SwParams& P, int NS, int EPL, int grid, cudaStream_t st
   }
 }
 
-int seqwarp_ctas_per_sm(int NS) { return NS == 1 ? 28 : NS == 2 ? 20 : 12; }  // CTA = one warp
+// resident warps (CTA = one warp) per SM: registers (28 / 20 by the launch bounds) or the row ring in shared memory
+int seqwarp_ctas_per_sm(int NS, int EPL) {
+  static int cache[3][9] = {};
+  int& c = cache[NS][EPL];
+  if (c == 0) {
+    switch (EPL) {
+      case 1: c = seqwarp_occupancy_epl<1>(NS); break;
+      case 2: c = seqwarp_occupancy_epl<2>(NS); break;
+      case 3: c = seqwarp_occupancy_epl<3>(NS); break;
+      case 4: c = seqwarp_occupancy_epl<4>(NS); break;
+      case 5: c = seqwarp_occupancy_epl<5>(NS); break;
+      case 6: c = seqwarp_occupancy_epl<6>(NS); break;
+      case 7: c = seqwarp_occupancy_epl<7>(NS); break;
+      default: c = seqwarp_occupancy_epl<8>(NS); break;
+    }
+    if (c <= 0) c = NS == 1 ? 24 : 16;
+  }
+  return c;
+}
 
 }  // namespace nbctc

@@ -2,4 +2,5 @@
 #include "seqwarp_kernel.cuh"
 namespace nbctc {
 template int launch_seqwarp_epl<3>(const SwParams&, int, int, cudaStream_t);
+template int seqwarp_occupancy_epl<3>(int);
 }

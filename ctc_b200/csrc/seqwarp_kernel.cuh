@@ -46,14 +46,14 @@ struct SwParams {
   float* row_lse_out;       // (T,B) or null: row log-partitions handed to the caller
   int K;                // tiles = ceil(T / 4)
   int Tp;
-  int pf_mode;          // bit 1: per-line L1 prefetch of the next tile's rows, checkpoint and log-partitions
-  int pf_near;          // tiles between the L1 prefetch and the loads
 };
 
 int launch_seqwarp(const SwParams& P, int NS, int EPL, int grid, cudaStream_t stream);
 template <int EPL>
 int launch_seqwarp_epl(const SwParams& P, int NS, int grid, cudaStream_t stream);
-int seqwarp_ctas_per_sm(int NS);
+template <int EPL>
+int seqwarp_occupancy_epl(int NS);  // resident CTAs (= warps) per SM of that instance
+int seqwarp_ctas_per_sm(int NS, int EPL);
 
 #ifdef __CUDACC__
 namespace sw {
@@ -359,7 +359,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
   const int Kf = Tb / kTT;  // full tiles
   // L1 prefetch: lane = (row of a tile, 128-byte line of the row); ONE instruction requests a whole tile, pf_near tiles
   // ahead of its loads (measured: L2 prefetches further ahead, per line or as TMA bulk prefetch, only cost time)
-  const bool pf_l1 = P.pf_mode & 2;
+  const bool pf_l1 = true;
   const int LW = min((C * 4 + 127) / 128 + 1, 8);  // lanes per row: lines 0, 128, ... and the row's last element
   const bool pf_lane = lane < kTT * LW;
   const int pf_ri = lane / LW, pf_off = min((lane - pf_ri * LW) * 128, C * 4 - 4);
@@ -387,7 +387,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
         for (int j = 0; j < NS; ++j) xg[i][j] = ldg_f(rq + goff[j]);
         rq += strideT;
       }
-      if (pf_l1 && pf_lane && k + P.pf_near < Kf) pf_tile(k + P.pf_near);
+      if (pf_l1 && pf_lane && k + 1 < Kf) pf_tile(k + 1);
       float nm[kTT], s[kTT];
 #pragma unroll
       for (int i = 0; i < kTT; ++i) nm[i] = -kL2E * row_max(xr[i]);
@@ -563,18 +563,14 @@ __device__ void Seq<NS, EPL>::run(int b) {
     // rows of the first tiles are still in L2 (phase 1 has just read them); request the ones further down
     const float* rl = row0 + (int64_t)(Kf * kTT - 1) * strideT;  // next row to load, walking down
     int since = 0;                                              // tiles since the last beta rescale
+    // the tile's checkpoint, lane scale and log-partitions are loaded one tile ahead of their use
+    double xa_n[NS];
+    int ea_n;
+    float4 l4_n;
+    load_ck(Kf - 1, xa_n, ea_n);
+    l4_n = *reinterpret_cast<const float4*>(lse_ws + (Kf - 1) * kTT);
     for (int k = Kf - 1; k >= 0; --k) {
-      if (pf_l1 && pf_lane && k >= P.pf_near) pf_tile(k - P.pf_near);
-      if (k > 0) {
-        // the tile's checkpoint, lane scales and log-partitions one tile ahead
-        if (pf_l1 && lane >= 28) {
-          const char* a = lane == 28 ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad)
-                        : lane == 29 ? reinterpret_cast<const char*>(ckx - lane * NS + (int64_t)(k - 1) * Lpad) + 128 * NS
-                        : lane == 30 ? reinterpret_cast<const char*>(cke - lane + ((k - 1) >> 1) * 32)
-                                     : reinterpret_cast<const char*>(lse_ws + (k - 1) * kTT);
-          pf_line_l1(a);
-        }
-      }
+      if (pf_l1 && pf_lane && k >= 1) pf_tile(k - 1);
       float xg[kTT][NS];
       {
         const float* rg = rl;
@@ -588,11 +584,15 @@ __device__ void Seq<NS, EPL>::run(int b) {
       float xr[2][EPL];  // the row being worked on and the next one down
       load_row(rl, xr[(kTT - 1) & 1]);
       double xa[NS], ga, gb, faca;
-      int ea;
-      load_ck(k, xa, ea);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xa[j] = xa_n[j];
+      const int ea = ea_n;
+      const float nl[kTT] = {-l4_n.x, -l4_n.y, -l4_n.z, -l4_n.w};
+      if (k > 0) {
+        load_ck(k - 1, xa_n, ea_n);
+        l4_n = *reinterpret_cast<const float4*>(lse_ws + (k - 1) * kTT);
+      }
       gscales(ea, ga, gb, faca);
-      const float4 l4 = *reinterpret_cast<const float4*>(lse_ws + k * kTT);
-      const float nl[kTT] = {-l4.x, -l4.y, -l4.z, -l4.w};
       float pe[kTT][NS];
       double a[kTT][NS];
 #pragma unroll
@@ -648,6 +648,14 @@ int launch_one(const SwParams& P, int grid, cudaStream_t stream) {
 }
 
 }  // namespace sw
+
+template <int EPL>
+int seqwarp_occupancy_epl(int NS) {
+  int n = 0;
+  cudaError_t e = NS == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sw::seqwarp_kernel<1, EPL>, sw::kWarps * 32, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sw::seqwarp_kernel<2, EPL>, sw::kWarps * 32, 0);
+  return e == cudaSuccess ? n : 0;
+}
 
 template <int EPL>
 int launch_seqwarp_epl(const SwParams& P, int NS, int grid, cudaStream_t stream) {
