@@ -39,6 +39,7 @@ SIGNATURES = {
     "nbctc_match_time_i32": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "nbctc_match_frame_i32": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "nbctc_host_release": (_int, [_int]),
+    "nbctc_debug_set_prof": (_int, [_vp]),
     "nbctc_loss_grad_host_f32": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _u32]),
     "nbbctc_loss_grad_host_f32": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _u32]),
 }

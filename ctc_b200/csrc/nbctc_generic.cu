@@ -22,6 +22,8 @@ struct GenericWs {
   float* emis;    // (T,B,Lmax) raw emission, overwritten by gamma
   double* alpha;  // (T,B,Lmax)
   int* bad;       // (B) label-out-of-range flag
+  int* rank;      // (B,Lmax) single-label: number of earlier states with the same label (scatter rounds of the gradient)
+  int* maxrank;   // (B)
   const int* gate;  // null, or: run only if *gate != 0 (the tiled multi-label path declined the call, nbctc_bin.cu)
 };
 
@@ -33,12 +35,16 @@ __host__ size_t carve(GenericWs* w, void* base, int64_t T, int64_t B, int64_t Lm
     return o;
   };
   size_t o_bad = take(sizeof(int) * B);
+  size_t o_rank = take(sizeof(int) * B * Lmax);
+  size_t o_maxrank = take(sizeof(int) * B);
   size_t o_rowc = take(sizeof(float) * T * B);
   size_t o_emis = take(sizeof(float) * T * B * Lmax);
   size_t o_alpha = take(sizeof(double) * T * B * Lmax);
   if (w) {
     char* c = static_cast<char*>(base);
     w->bad = reinterpret_cast<int*>(c + o_bad);
+    w->rank = reinterpret_cast<int*>(c + o_rank);
+    w->maxrank = reinterpret_cast<int*>(c + o_maxrank);
     w->rowc = reinterpret_cast<float*>(c + o_rowc);
     w->emis = reinterpret_cast<float*>(c + o_emis);
     w->alpha = reinterpret_cast<double*>(c + o_alpha);
@@ -121,6 +127,23 @@ __device__ __forceinline__ void lattice_body(const Problem& p, const GenericWs& 
   double* a0 = sm;
   double* a1 = sm + L;
   const int nt = blockDim.x;
+  if (p.labels != nullptr && p.grad != nullptr) {
+    // duplicate rank of every state: the gradient kernel subtracts the gammas of one label in rank rounds, i.e. in
+    // ascending state order without atomics (repeated labels accumulate; bit-reproducible)
+    __shared__ int s_maxrank;
+    if (threadIdx.x == 0) s_maxrank = 0;
+    __syncthreads();
+    const int32_t* lab = p.labels + b * L;
+    for (int64_t s = threadIdx.x; s < Lb; s += nt) {
+      const int32_t l = lab[s];
+      int r = 0;
+      for (int64_t s2 = 0; s2 < s; ++s2) r += lab[s2] == l;
+      w.rank[b * L + s] = r;
+      if (r) atomicMax(&s_maxrank, r);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) w.maxrank[b] = s_maxrank;
+  }
   // ---- alpha ----
   for (int64_t s = threadIdx.x; s < Lb; s += nt) {
     double v = (s == 0) ? (double)w.emis[(0 * B + b) * L] - (double)w.rowc[b] : -INFINITY;
@@ -217,9 +240,14 @@ grad_kernel(Problem p, GenericWs w) {
     const float lse = w.rowc[row];
     for (int64_t c = lane; c < p.C; c += 32) g[c] = wgt * expf(x[c] - lse);
     __syncwarp();
-    for (int64_t s = lane; s < Lb; s += 32) {
-      int32_t l = p.labels[b * p.Lmax + s];
-      atomicAdd(&g[l], -wgt * gam[s]);
+    const int mr = w.maxrank[b];
+    for (int r = 0; r <= mr; ++r) {  // one state per label and round: plain read-modify-writes, ascending state order
+      for (int64_t s = lane; s < Lb; s += 32)
+        if (w.rank[b * p.Lmax + s] == r) {
+          const int32_t l = p.labels[b * p.Lmax + s];
+          g[l] -= wgt * gam[s];
+        }
+      __syncwarp();
     }
   } else {
     wgt /= (float)p.C;

@@ -11,7 +11,7 @@
 //     sum_s alpha_t(s) beta_t(s) = Z holds to 1e-13 so gamma needs no per-row normalisation.  Phase 1 stores
 //     one alpha checkpoint per tile; phase 2 walks the tiles downwards, replays alpha inside the tile next to
 //     the beta recursion (the reference's backward pass is commented out at NoBlankCTC.py:113-125; autograd
-//     does it), and the row warps add -w*gamma to the gradient rows with global float reductions.
+//     does it), and the row warps add -w*gamma to the gradient rows in shared memory, in conflict-free rank rounds.
 //   * the two roles advance in lock step, one __syncthreads() per tile; nobody polls.
 //
 // This file: shape -> launch plan (states per lane, lanes per row, group size, shared-memory carve-up),

@@ -235,6 +235,12 @@ int nbbctc_loss_grad_host_f32(int device, const float* logits_host, int64_t T, i
 /* Number of kernels this library has launched in the calling process (diagnostics / bench). */
 uint64_t nbctc_kernel_launch_count(void);
 
+/*
+ * Development hook, not part of the operator interface: device buffer for the per-role cycle counters of the lock-step
+ * kernel.  Only builds with -DNBCTC_PROF write to it (tools/prof_roles.py); the product build ignores the pointer.
+ */
+int nbctc_debug_set_prof(long long* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

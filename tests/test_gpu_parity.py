@@ -483,3 +483,15 @@ def test_aligned16_flag_contract(nb):
             ws.data_ptr(), full)
     rc = lib.nbctc_loss_grad_f32(*args, _ffi.FLAG_ALIGNED16, torch.cuda.current_stream().cuda_stream)
     assert rc == -1 and b"16-byte aligned" in lib.nbctc_last_error()
+
+
+@pytest.mark.parametrize("flags", [1, 8, 32], ids=["generic", "lockstep", "seqwarp"])
+def test_repeated_labels_are_bit_reproducible(nb, flags):
+    """the gammas of states that share a class accumulate.  Every path adds them in ascending state
+    order (rank rounds / follower walk, no atomics): two runs give identical bits."""
+    T, B, C, L = 60, 40, 7, 32
+    x, lab, il, tl = make_ctc_case(77, T, B, C, L, dup=True, Lmin=16)
+    l1, g1 = run_cuda(nb, "ctc", x, lab, il, tl, flags=flags)
+    l2, g2 = run_cuda(nb, "ctc", x, lab, il, tl, flags=flags)
+    assert np.array_equal(l1, l2) and np.array_equal(g1, g2)
+    assert_parity(l1, g1, oracle("ctc", x, lab, il, tl))
