@@ -36,7 +36,7 @@ def scaled(k):  # bytes / time metrics come with a unit prefix
     if v is None:
         return None
     u = val[k][1]
-    mul = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}.get(u, 1)
+    mul = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}.get(u.split("/")[0], 1)
     return v * mul
 
 
