@@ -286,7 +286,9 @@ __device__ void Seq<NS, EPL>::run(int b) {
   const int T = (int)p.T, B = (int)p.B;
   const int64_t Tb64 = p.in_len[b], Lb64 = p.tgt_len[b];
   bool feas = seq_feasible(Tb64, Lb64, p.T, p.Lmax) && Lb64 <= Lpad;
-  const int Tb = feas ? (int)Tb64 : 0, Lb = feas ? (int)Lb64 : 0;
+  // (warp reductions of warp-uniform values: the compiler then KNOWS they are uniform, keeps them in uniform registers
+  // and drops the divergence guards around every shuffle inside the loops they bound)
+  const int Tb = __reduce_max_sync(kFull, feas ? (int)Tb64 : 0), Lb = __reduce_max_sync(kFull, feas ? (int)Lb64 : 0);
 
   // ---- labels, repeated labels
   int lab[NS];
