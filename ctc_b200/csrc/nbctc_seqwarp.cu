@@ -89,11 +89,17 @@ SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   pl.o_order = off;
   off = align_up(off + sizeof(int) * (size_t)B, 256);
   pl.o_lse = off;
-  off = align_up(off + sizeof(float) * (size_t)B * pl.Tp, 256);
-  pl.o_ckx = off;
-  off = align_up(off + sizeof(double) * (size_t)B * pl.K * 32 * pl.NS, 256);
-  pl.o_cke = off;
-  off = align_up(off + sizeof(int) * (size_t)B * (pl.K / 2 + 1) * 32, 256);
+  if (pl.wide) {
+    off = align_up(off + sizeof(float) * (size_t)B * pl.Tp, 256);
+    pl.o_ckx = off;
+    off = align_up(off + sizeof(double) * (size_t)B * pl.K * 32 * pl.NS, 256);
+    pl.o_cke = off;
+    off = align_up(off + sizeof(int) * (size_t)B * (pl.K / 2 + 1) * 32, 256);
+  } else {  // one record per sequence (seqwarp_launch)
+    const size_t rec = align_up(align_up(align_up(sizeof(float) * (size_t)pl.Tp, 128) + sizeof(int) * (size_t)(pl.K / 2 + 1) * 32, 256) +
+                                    sizeof(double) * (size_t)pl.K * 32 * pl.NS, 256);
+    off = align_up(off + rec * (size_t)B, 256);
+  }
   pl.bytes = off;
   pl.ok = true;
   return pl;
@@ -161,9 +167,14 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
   }
   SwParams P{};
   P.p = p;
-  P.lse2 = reinterpret_cast<float*>(w + pl.o_lse);
-  P.ckx = reinterpret_cast<double*>(w + pl.o_ckx);
-  P.cke = reinterpret_cast<int*>(w + pl.o_cke);
+  // the three per-sequence arrays interleaved into one record per sequence (same total size as the separate arrays)
+  P.rec = w + pl.o_lse;
+  {
+    const size_t lse_b = sizeof(float) * (size_t)pl.Tp, cke_b = sizeof(int) * (size_t)(pl.K / 2 + 1) * 32;
+    P.o_cke = (int)align_up(lse_b, 128);
+    P.o_ckx = (int)align_up(P.o_cke + cke_b, 256);
+    P.rec_bytes = (int64_t)align_up(P.o_ckx + sizeof(double) * (size_t)pl.K * 32 * pl.NS, 256);
+  }
   P.row_lse_in = row_lse_in;
   P.row_lse_out = row_lse_out;
   P.K = pl.K;

@@ -37,9 +37,13 @@ namespace nbctc {
 
 struct SwParams {
   Problem p;
-  float* lse2;          // [B][Tp] row log2-partitions, Tp = 4 K
-  double* ckx;          // [B][K][32 NS] alpha before the first step of tile k (k >= 1)
-  int* cke;             // [B][K/2 + 1][32] lane scales of the alpha state after the rescale in front of tile 2r
+  // per-sequence record in the workspace (rec_bytes apart; ONE base pointer per warp, 32-bit offsets from it):
+  //   [0, 4 Tp)              row log2-partitions, Tp = 4 K
+  //   [o_cke, + 128 (K/2+1)) lane scales of the alpha state after the rescale in front of tile 2r
+  //   [o_ckx, + 256 NS K)    alpha before the first step of tile k (k >= 1)
+  char* rec;
+  int64_t rec_bytes;
+  int o_cke, o_ckx;
   const int* order;     // null: sequence = ticket; else the longest-first order of the prep kernel
   int* ticket;          // null: one sequence per warp (B <= warps of the grid); else the work queue
   const float* row_lse_in;  // (T,B) or null: row log-partitions supplied by the producer of the logits
@@ -346,9 +350,10 @@ __device__ void Seq<NS, EPL>::run(int b) {
   int goff[NS];                                                 // label's class relative to the lane's first class
 #pragma unroll
   for (int j = 0; j < NS; ++j) goff[j] = lab[j] - lane;
-  float* const lse_ws = P.lse2 + (int64_t)b * P.Tp;
-  double* const ckx = P.ckx + ((int64_t)b * P.K * 32 + lane) * NS;
-  int* const cke = P.cke + (int64_t)b * (P.K / 2 + 1) * 32 + lane;
+  char* const rec = P.rec + (int64_t)b * P.rec_bytes;
+  float* const lse_ws = reinterpret_cast<float*>(rec);
+  double* const ckx = reinterpret_cast<double*>(rec + P.o_ckx) + lane * NS;
+  int* const cke = reinterpret_cast<int*>(rec + P.o_cke) + lane;
 
   // ================================================================ phase 1: alpha
   // start pattern (-1)^s: the first step turns it into alpha_0 = (p_0(0), 0, 0, ...) exactly, without a special case
@@ -414,7 +419,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
       }
       if (want_grad && ck_lane) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) ckx[(int64_t)k * Lpad + j] = x[j];
+        for (int j = 0; j < NS; ++j) ckx[k * Lpad + j] = x[j];
       }
     }
 #pragma unroll
@@ -431,7 +436,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
       }
       if (want_grad && ck_lane) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) ckx[(int64_t)k * Lpad + j] = x[j];
+        for (int j = 0; j < NS; ++j) ckx[k * Lpad + j] = x[j];
       }
     }
     for (int i = 0; i < nrem; ++i) {
@@ -516,7 +521,7 @@ __device__ void Seq<NS, EPL>::run(int b) {
       for (int j = 0; j < NS; ++j) xa[j] = ((lane * NS + j) & 1) ? -1.0 : 1.0;
     } else {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) xa[j] = ck_lane ? ckx[(int64_t)k * Lpad + j] : 0.0;
+      for (int j = 0; j < NS; ++j) xa[j] = ck_lane ? ckx[k * Lpad + j] : 0.0;
       if (k >= 2 && ck_lane) ea = cke[(k >> 1) * 32];
     }
   };
