@@ -370,9 +370,15 @@ __device__ void Seq<NS, EPL>::run(int b) {
   const int LW = min((C * 4 + 127) / 128 + 1, 8);  // lanes per row: lines 0, 128, ... and the row's last element
   const bool pf_lane = lane < kTT * LW;
   const int pf_ri = lane / LW, pf_off = min((lane - pf_ri * LW) * 128, C * 4 - 4);
-  const char* const pf_base = reinterpret_cast<const char*>(p.logits + (int64_t)b * C) + pf_off;  // + t * strideT * 4
-  const int64_t strideB = strideT * 4;
-  auto pf_tile = [&](int kk) { pf_line_l1(pf_base + (int64_t)(kk * kTT + pf_ri) * strideB); };
+  // byte offsets from the running row pointers (32 bits: B C < 2^26, host gate): phase 1 from the next tile's first row,
+  // phase 2 from the tile's last row to the tile below
+  const int strideB = (int)strideT * 4;
+  const int pf_d1 = pf_ri * strideB + pf_off - 4 * lane, pf_d2 = pf_d1 - (2 * kTT - 1) * strideB;
+  // (at one state per lane the kernel sits on its 72-register limit and the absolute form below, which the compiler
+  // rebuilds from the kernel arguments, measures 8 % faster there than the running-pointer form; at two states per lane
+  // it is the other way round)
+  const char* const pf_base = reinterpret_cast<const char*>(p.logits + (int64_t)b * C) + pf_off;
+  auto pf_tile = [&](int kk) { pf_line_l1(pf_base + (int64_t)(kk * kTT + pf_ri) * (strideT * 4)); };
   const float* rq = row0;  // first row of the tile
   for (int k = 0; k < Kf; ++k) {
     float xg[kTT][NS];
@@ -394,7 +400,10 @@ __device__ void Seq<NS, EPL>::run(int b) {
         for (int j = 0; j < NS; ++j) xg[i][j] = ldg_f(rq + goff[j]);
         rq += strideT;
       }
-      if (pf_l1 && pf_lane && k + 1 < Kf) pf_tile(k + 1);
+      if (pf_l1 && pf_lane && k + 1 < Kf) {
+        if (NS == 1) pf_tile(k + 1);
+        else pf_line_l1(reinterpret_cast<const char*>(rq) + pf_d1);
+      }
       float nm[kTT], s[kTT];
 #pragma unroll
       for (int i = 0; i < kTT; ++i) nm[i] = -kL2E * row_max(xr[i]);
@@ -577,7 +586,10 @@ __device__ void Seq<NS, EPL>::run(int b) {
     load_ck(Kf - 1, xa_n, ea_n);
     l4_n = *reinterpret_cast<const float4*>(lse_ws + (Kf - 1) * kTT);
     for (int k = Kf - 1; k >= 0; --k) {
-      if (pf_l1 && pf_lane && k >= 1) pf_tile(k - 1);
+      if (pf_l1 && pf_lane && k >= 1) {
+        if (NS == 1) pf_tile(k - 1);
+        else pf_line_l1(reinterpret_cast<const char*>(rl) + pf_d2);
+      }
       float xg[kTT][NS];
       {
         const float* rg = rl;
