@@ -213,11 +213,12 @@ int host_entry(int device, bool binary, const float* logits_h, int64_t T, int64_
     h.init = true;
   }
   const bool want_grad = grad_h != nullptr && !(flags & NBCTC_FLAG_NO_GRAD);
-  // chunk of sequences: ~64 MB of logits, a multiple of 4 sequences (16-byte aligned slabs for any C), >= 8 chunks
+  // chunk of sequences: ~64 MB of logits, a multiple of 4 sequences (16-byte aligned slabs for any C), >= 16 chunks
   // for a large batch so that the copies of neighbouring chunks hide the kernel
   const int64_t row_bytes = T * C * 4;
   int64_t Bc = std::max<int64_t>(4, (int64_t)(64e6 / (double)row_bytes) / 4 * 4);
-  Bc = std::min(Bc, std::max<int64_t>(4, ((B + 7) / 8 + 3) / 4 * 4));
+  static const int min_chunks = [] { const char* v = getenv("NBCTC_HOST_CHUNKS"); return v ? std::max(1, atoi(v)) : 16; }();
+  Bc = std::min(Bc, std::max<int64_t>(4, ((B + min_chunks - 1) / min_chunks + 3) / 4 * 4));
   Bc = std::min(Bc, B);
   const int64_t nchunk = (B + Bc - 1) / Bc;
   const size_t tg_per_seq = (size_t)Lmax * (binary ? (size_t)C : 1) * sizeof(TargetT);

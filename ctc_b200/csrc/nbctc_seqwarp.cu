@@ -98,6 +98,7 @@ SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   } else {  // one record per sequence (seqwarp_launch)
     const size_t rec = align_up(align_up(align_up(sizeof(float) * (size_t)pl.Tp, 128) + sizeof(int) * (size_t)(pl.K / 2 + 1) * 32, 256) +
                                     sizeof(double) * (size_t)pl.K * 32 * pl.NS, 256);
+    if (rec >= ((size_t)1 << 30)) return pl;  // 32-bit offsets inside a record
     off = align_up(off + rec * (size_t)B, 256);
   }
   pl.bytes = off;
