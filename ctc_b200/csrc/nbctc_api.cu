@@ -66,7 +66,8 @@ bool want_seqwarp(uint32_t flags, int64_t T, int64_t B, int64_t C, int64_t Lmax)
   if (!seqwarp_supported(T, B, C, Lmax)) return false;
   if (flags & kPathFlags) return (flags & NBCTC_FLAG_SEQWARP) != 0;
   if (env_path()) return env_path() == 3;
-  return B >= (seqwarp_is_wide(T, B, C, Lmax) ? 640 : Lmax <= 32 ? 3072 : 2560);
+  // measured cross-overs against the lock-step kernel (gpurun_out/thresholds.log: T=256/512/1024 at the three shape classes)
+  return B >= (seqwarp_is_wide(T, B, C, Lmax) ? 384 : Lmax <= 32 ? 2304 : 1536);
 }
 
 int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void* tg, int64_t Lmax,

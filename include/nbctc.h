@@ -57,7 +57,7 @@ extern "C" {
 #define NBCTC_FLAG_SEQWARP 32u    /* single-label variant: the sequence-per-warp kernels (seqwarp_kernel.cuh: C <= 256, Lmax <= 64;
                                      seqwide_kernel.cuh: C % 4 == 0, C <= 1024, Lmax <= 256, 16-byte aligned tensors).
                                      Without a path flag they take the batches that fill the GPU with one sequence per
-                                     warp (>= 3072 / 2560 / 640 sequences); smaller batches stay on the lock-step kernel */
+                                     warp (>= 2304 / 1536 / 384 sequences); smaller batches stay on the lock-step kernel */
 
 typedef void* nbctc_stream_t; /* cudaStream_t */
 

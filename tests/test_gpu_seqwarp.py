@@ -143,7 +143,7 @@ def test_row_lse_rejected_on_wide_rows():
 
 
 def test_default_dispatch_takes_the_seqwarp_kernel_for_large_batches():
-    """B >= 3072 sequences of the narrow shape run the sequence-per-warp kernel by default: same bits as the forced path."""
+    """B >= 2304 sequences of the narrow shape run the sequence-per-warp kernel by default: same bits as the forced path."""
     import ctc_b200
     T, B, C, Lmax = 12, 3200, 20, 6
     x, lab, il, tl = make_ctc_case(13, T, B, C, Lmax)

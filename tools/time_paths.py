@@ -12,7 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ctc_b200 import _ffi  # noqa: E402
 
 SHAPES = {"cfg2": (256, 4096, 157, 32, False), "cfg2r": (256, 4096, 157, 32, True), "cfg5": (512, 8192, 157, 64, False),
-          "cfg1": (64, 8, 157, 8, False), "cfg4": (4096, 1024, 1024, 256, False), "cfg4q": (1024, 1024, 1024, 256, False), "cfg4s": (512, 1024, 1024, 256, False), "cfg5s": (512, 4096, 157, 64, False), "b1024": (256, 1024, 157, 32, False), "b2048": (256, 2048, 157, 32, False)}
+          "cfg1": (64, 8, 157, 8, False), "cfg4": (4096, 1024, 1024, 256, False), "cfg4q": (1024, 1024, 1024, 256, False), "cfg4s": (512, 1024, 1024, 256, False), "cfg5s": (512, 4096, 157, 64, False), "b1024": (256, 1024, 157, 32, False), "b2048": (256, 2048, 157, 32, False), "b3072": (256, 3072, 157, 32, False),
+          "b1536": (256, 1536, 157, 32, False), "w256": (1024, 256, 1024, 256, False), "w512": (1024, 512, 1024, 256, False), "w768": (1024, 768, 1024, 256, False),
+          "m1024": (512, 1024, 157, 64, False), "m2048": (512, 2048, 157, 64, False), "m3072": (512, 3072, 157, 64, False)}
 
 
 def main():
