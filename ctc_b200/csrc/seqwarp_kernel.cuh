@@ -2,8 +2,9 @@
 // nbctc_seqwarp.cu).
 //
 // ONE warp owns ONE sequence from the first row to the last gradient store: no CTA barrier, no shared-memory hand-off
-// between roles, nothing to poll.  A (t,b) row of the (T,B,C) logits is read with EPL coalesced 4-byte loads per lane
-// (lane l holds classes l, l+32, ...), kept in registers one tile of 4 time steps ahead of its use, and the L lattice
+// between roles, nothing to poll.  A CTA is one warp, so everything derived from blockIdx is provably warp-uniform.  A
+// (t,b) row of the (T,B,C) logits is read with EPL coalesced 4-byte loads per lane (lane l holds classes l, l+32, ...),
+// a tile of 4 time steps at a time, after one prefetch.global.L1 per tile has requested it a tile ahead; the L lattice
 // states sit NS per lane in float64.  All B sequences of a batch are in flight at once (28 warps per SM at NS = 1), so
 // the latency of one sequence's dependent chain is hidden by the other warps of the SM instead of by warp
 // specialisation, and the whole GPU streams through the logits time step by time step.
@@ -11,8 +12,8 @@
 //   phase 1 (t upwards)    row log-partition (NoBlankCTC.py:136): max by one warp REDUX, the sums of the 4 rows of a
 //                          tile in ONE shared butterfly; emissions p_t(s) = softmax(x_t)[label_s] (NoBlankCTC.py:96-102)
 //                          from a per-lane gather load; alpha step (NoBlankCTC.py:71-87) = one 64-bit shuffle + DFMA +
-//                          DMUL.  Kept for phase 2: the row log-partitions (4 bytes per row) and one alpha checkpoint
-//                          per tile.
+//                          DMUL.  Kept for phase 2, in one workspace record per sequence: the row log-partitions
+//                          (4 bytes per row), one alpha checkpoint per tile (active lanes only) and the lane scales.
 //   phase 2 (t downwards)  the rows again (L2 hit for the last steps, HBM for the rest: 3 passes over N bytes instead
 //                          of the lock-step kernel's 2, but at streaming speed and for any T), alpha replayed inside the
 //                          tile from its checkpoint, beta backwards (the reference's own backward pass is commented out
