@@ -18,6 +18,7 @@ FLAG_ALIGNED16 = 4
 FLAG_LOCKSTEP = 8
 FLAG_PIPELINE = 16
 FLAG_SEQWARP = 32
+FLAG_SUM_WEIGHTED = 64
 
 _lib = None
 

@@ -47,6 +47,7 @@ struct Problem {
   float* grad;               // (T,B,C) or null
   const float* seq_w;        // (B) or null
   float w_scalar;
+  bool sum_weighted;         // loss_sum = w_scalar * sum_b seq_w[b] * loss[b] (float64) instead of the plain sum
   int64_t T, B, C, Lmax;
 };
 

@@ -90,6 +90,7 @@ int check_common(const void* logits, int64_t T, int64_t B, int64_t C, const void
 int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t stream, const float* row_lse_in = nullptr,
         float* row_lse_out = nullptr) {
   if (flags & NBCTC_FLAG_NO_GRAD) p.grad = nullptr;
+  p.sum_weighted = (flags & NBCTC_FLAG_SUM_WEIGHTED) != 0;
   int rc;
   bool use_sw = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_seqwarp(flags, p.T, p.B, p.C, p.Lmax);
   // the wide-row variant moves rows with TMA: 16-byte aligned tensors only (else the paths below)

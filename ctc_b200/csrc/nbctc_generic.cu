@@ -452,7 +452,7 @@ grad_bin_smem_kernel(Problem p, GenericWs w, int Cp, int64_t nchunk) {
 }
 
 __global__ void reduce_loss_kernel(const float* __restrict__ loss, const float* __restrict__ seq_w, float w_scalar,
-                                   int64_t B, double* __restrict__ sum_out, float* __restrict__ reduced_out) {
+                                   int64_t B, double* __restrict__ sum_out, float* __restrict__ reduced_out, bool sum_weighted) {
   // one CTA, fixed-order tree => bit-reproducible
   __shared__ double sh[2][32];
   double acc = 0.0, wacc = 0.0;
@@ -470,7 +470,7 @@ __global__ void reduce_loss_kernel(const float* __restrict__ loss, const float* 
     double v = warp_sum(in ? sh[0][threadIdx.x] : 0.0);
     double wv = warp_sum(in ? sh[1][threadIdx.x] : 0.0);
     if (threadIdx.x == 0) {
-      if (sum_out) *sum_out = v;
+      if (sum_out) *sum_out = sum_weighted ? wv * (double)w_scalar : v;
       if (reduced_out) *reduced_out = (float)(wv * (double)w_scalar);
     }
   }
@@ -484,7 +484,7 @@ size_t generic_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
 }
 
 int reduce_loss_launch(const Problem& p, cudaStream_t stream) {
-  reduce_loss_kernel<<<1, 1024, 0, stream>>>(p.loss, p.seq_w, p.w_scalar, p.B, p.loss_sum, p.loss_reduced);
+  reduce_loss_kernel<<<1, 1024, 0, stream>>>(p.loss, p.seq_w, p.w_scalar, p.B, p.loss_sum, p.loss_reduced, p.sum_weighted);
   NBCTC_LAUNCH_CHECK();
   return NBCTC_OK;
 }

@@ -31,14 +31,18 @@ class _AllReduceSumAsync(torch.autograd.Function):
     wait for it, so the next step's kernels overlap the all-reduce latency.  The handle is kept on ``holder``."""
 
     @staticmethod
-    def forward(ctx, x, group, holder):
-        y = x.detach().clone()
+    def forward(ctx, x, group, holder, inplace):
+        if inplace:          # x is a fresh buffer nobody else reads (the loss call's own output): reduce it where it is
+            ctx.mark_dirty(x)
+            y = x
+        else:
+            y = x.detach().clone()
         holder.append(dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group, async_op=True))
         return y
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None
+        return g, None, None, None
 
 
 class _Done:
@@ -46,17 +50,19 @@ class _Done:
         return True
 
 
-def all_reduce_sum_async(x: torch.Tensor, group=None):
+def all_reduce_sum_async(x: torch.Tensor, group=None, inplace: bool = False):
     """Autograd-transparent all-reduce(sum) that does not block the current stream.
 
     Returns ``(y, work)``.  ``y.backward()`` may be called at once (the gradient of a sum over ranks does not depend
     on its value); ``work.wait()`` must be called before ``y`` is READ on the current stream (it makes that stream
-    wait for the collective, not the host).  With one rank: ``(x, <no-op handle>)``.
+    wait for the collective, not the host).  With one rank: ``(x, <no-op handle>)``.  ``inplace=True`` reduces ``x``'s own
+    buffer (no copy kernel in front of the collective): for the output of ``no_blank_ctc_loss(..., out64=True)``, which
+    nobody else holds.
     """
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return x, _Done()
     holder = []
-    y = _AllReduceSumAsync.apply(x, group, holder)
+    y = _AllReduceSumAsync.apply(x, group, holder, bool(inplace) and not x.is_leaf)
     return y, holder[0]
 
 
@@ -97,7 +103,7 @@ class ShardedLoss(torch.nn.Module):
             total_batch = logits.shape[1] * world      # equal shards
         local = self.local_sum_fn(logits, targets, input_length, target_length, total_batch)
         if self.async_reduce:
-            return all_reduce_sum_async(local, self.group)
+            return all_reduce_sum_async(local, self.group, inplace=True)
         return all_reduce_sum(local, self.group).to(torch.float32)
 
 

@@ -107,6 +107,8 @@ class _NoBlankCTCFunction(torch.autograd.Function):
         want_grad = bool(want_grad) and bool(ctx.needs_input_grad[0])
         nb = int(total_batch) if total_batch else B
         w = 1.0 / nb if reduction == "mean" else 1.0
+        if out64 and reduction != "none":
+            flags = int(flags) | _ffi.FLAG_SUM_WEIGHTED   # the kernel writes w * sum in float64: no torch op after the call
         per_seq, loss_sum, reduced, grad = _launch(x, tg, il, tl, binary, want_grad, w, None, int(flags))
         ctx.grad = grad
         ctx.per_seq_out = reduction == "none"
@@ -115,7 +117,7 @@ class _NoBlankCTCFunction(torch.autograd.Function):
         if reduction == "none":
             return per_seq
         if out64:
-            return loss_sum * w
+            return loss_sum
         return reduced
 
     @staticmethod

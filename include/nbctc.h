@@ -59,6 +59,10 @@ extern "C" {
                                      Without a path flag they take the batches that fill the GPU with one sequence per
                                      warp (>= 2304 / 1536 / 384 sequences); smaller batches stay on the lock-step kernel */
 
+#define NBCTC_FLAG_SUM_WEIGHTED 64u /* loss_sum receives weight_scalar * sum_b seq_weights[b] * loss[b] in float64 (loss_reduced
+                                     without the rounding to float32) instead of the plain sum: the scalar a sharded run
+                                     all-reduces, with no extra kernel between the loss call and the collective */
+
 typedef void* nbctc_stream_t; /* cudaStream_t */
 
 /* Library version (NBCTC_VERSION of the build). */
