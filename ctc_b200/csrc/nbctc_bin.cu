@@ -21,10 +21,13 @@
 //
 // HBM traffic: logits read twice, gradient written once, emission/gamma tile (T,B,Lmax) fp32 written twice and read
 // twice, checkpoints (T/8,B,Lpad) f64 -- about 1.8x the algorithmic bytes at C = 157, Lmax = 32.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
+#include "seqwarp_kernel.cuh"  // sw:: chain steps, lane scales, reductions
 #include "stream_kernel.cuh"
 
 namespace nbctc {
@@ -42,11 +45,16 @@ struct TiledWs {
   double* ckpt;         // [B][NT][Lpad] alpha checkpoints
   int* cke;             // [B][NT][16]   their lane scales
   float* emis;          // (T,B,Lmax)    emissions p_t(s), overwritten by gamma
+  char* rec;            // K12 (Lmax <= 32): per sequence [K/2+1][32] int lane scales | [K][32] float64 alpha checkpoints
+  int64_t rec_bytes;
+  int o_rec_ckx;
   int LW, NT, Lpad;
 };
 
 struct Layout {
-  size_t o_cmask, o_ckpt, o_cke, o_emis, total;
+  size_t o_cmask, o_ckpt, o_cke, o_emis, o_rec, rec_bytes, total;
+  int o_rec_ckx;
+  bool seq;  // Lmax <= 32: emissions and lattice in ONE sequence-per-warp kernel (K12) instead of K1 + K2
   int LW, NT, Lpad;
 };
 
@@ -61,6 +69,13 @@ Layout layout(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   l.o_ckpt = take(sizeof(double) * (size_t)B * l.NT * l.Lpad);
   l.o_cke = take(sizeof(int) * (size_t)B * l.NT * 16);
   l.o_emis = take(sizeof(float) * (size_t)T * B * Lmax);
+  l.seq = Lmax <= 32 && T < (1 << 24);
+  if (l.seq) {
+    const size_t K = (size_t)((T + 3) / 4);
+    l.o_rec_ckx = (int)align_up(sizeof(int) * (K / 2 + 1) * 32, 256);
+    l.rec_bytes = align_up(l.o_rec_ckx + sizeof(double) * K * 32, 256);
+    l.o_rec = take(l.rec_bytes * (size_t)B);
+  }
   l.total = off;
   return l;
 }
@@ -215,6 +230,234 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
     }
     __syncwarp();
   }
+}
+
+// ------------------------------------------------------------------------------------ K12: emissions + lattice, one warp per sequence
+// Lmax <= 32 (BASELINE configs[2]): the sequence-per-warp scheme of seqwarp_kernel.cuh applied to the multi-label
+// variant.  One warp owns one sequence: class lists once; then, tile of 4 time steps by tile, the rows' softplus sums and
+// the emissions p_t(s) (lane = state; a class byte is decoded once and used for the 4 rows of the tile), the alpha
+// step in float64 with per-lane scales, p_t(s) parked in the (T,B,Lmax) tile; read-out; then downwards: p back from the
+// tile, alpha replayed from the tile's checkpoint, beta, gamma = alpha beta / Z over p in the tile -- what K3 consumes.
+// Against K1 + K2: the emission tile is written once and read once less, the lattice runs on all 32 lanes instead of
+// 16 + 16, and there is one launch and one pass over the label bookkeeping instead of two.
+template <int NCI>
+__global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
+  using namespace sw;
+  constexpr int Cp = 32 * NCI + 8;  // row stride: rows start 8 banks apart
+  __shared__ float xs[kTT * Cp];
+  __shared__ __align__(16) uint32_t sl[32 * 8];
+  const int lane = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const int64_t Tb64 = p.in_len[b], Lb64 = p.tgt_len[b];
+  const bool feas = seq_feasible(Tb64, Lb64, p.T, p.Lmax);
+  const int Tb = __reduce_max_sync(kFull, feas ? (int)Tb64 : 0), Lb = __reduce_max_sync(kFull, feas ? (int)Lb64 : 0);
+  if (Tb == 0) {
+    if (lane == 0) p.loss[b] = INFINITY;
+    return;
+  }
+  const int C = (int)p.C, Lmax = (int)p.Lmax;
+  // ---- class lists of the states (as K1) and the class -> states masks of K3
+  {
+    bool any_bad = false;
+    for (int s = 0; s < Lb; ++s) {
+      const float* y = p.targets + ((size_t)b * Lmax + s) * C;
+      float yv[NCI];
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) yv[i] = (i + 1 < NCI || lane + 32 * i < C) ? __ldg(y + lane + 32 * i) : 0.f;
+      uint32_t* rec = sl + s * 8;
+      if (lane < 8) rec[lane] = 0u;
+      __syncwarp();
+      unsigned char* bytes = reinterpret_cast<unsigned char*>(rec);
+      int count = 0;
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) {
+        const int c = lane + 32 * i;
+        const bool one = yv[i] == 1.f;
+        bad |= !(one || yv[i] == 0.f);
+        const unsigned m = __ballot_sync(kFull, one);
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        if (one && pos < 31) bytes[1 + pos] = (unsigned char)c;
+        if (one) atomicOr(&w.cmask[((size_t)b * C + c) * w.LW], 1u << s);
+        count += __popc(m);
+      }
+      any_bad |= __any_sync(kFull, bad) || count > 31;
+      if (lane == 0) bytes[0] = (unsigned char)min(count, 31);
+    }
+    __syncwarp();
+    if (any_bad) {  // outside this path's domain: the gated generic kernels redo the call
+      if (lane == 0) atomicOr(w.flag, 1);
+      return;
+    }
+  }
+  const bool valid = lane < Lb;
+  uint32_t lw[8];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sl + (size_t)min(lane, Lb - 1) * 8);
+    const uint4 a = src[0], c4 = src[1];
+    lw[0] = a.x; lw[1] = a.y; lw[2] = a.z; lw[3] = a.w;
+    lw[4] = c4.x; lw[5] = c4.y; lw[6] = c4.z; lw[7] = c4.w;
+  }
+  const int n = valid ? (int)(lw[0] & 0xffu) : 0;
+  const int words = (__reduce_max_sync(kFull, n) + 4) >> 2;  // bytes 0..n
+  const float k2 = stream::kLog2e / (float)C;
+
+  const int64_t rstride = p.B * p.C, estride = p.B * (int64_t)Lmax;
+  float* const e_b = w.emis + b * Lmax + lane;
+  char* const rec = w.rec + b * w.rec_bytes;
+  int* const cke = reinterpret_cast<int*>(rec) + lane;
+  double* const ckx = reinterpret_cast<double*>(rec + w.o_rec_ckx) + lane;
+  const bool estore = lane < Lmax;
+  const bool want_grad = p.grad != nullptr;
+
+  // ================================================================ phase 1
+  double x[1] = {(lane & 1) ? -1.0 : 1.0};
+  int e = 0;
+  double fac = lane == 0 ? 0.0 : 1.0;
+  const int K = (Tb + kTT - 1) / kTT;
+  const float* xr = p.logits + b * p.C + lane;  // row t = 0
+  for (int k = 0; k < K; ++k) {
+    const int nrow = min(kTT, Tb - k * kTT);
+    float v[NCI][kTT];
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) {
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) v[i][r] = ((i + 1 < NCI || lane + 32 * i < C) && r < nrow) ? ldg_f(xr + 32 * i) : 0.f;
+      xr += rstride;
+    }
+    // sum_c softplus(x_c) = sum_c max(x_c, 0) + log prod_c (1 + exp(-|x_c|))  (K1)
+    float sp[kTT];
+    {
+      float pos[kTT], prod[kTT];
+#pragma unroll
+      for (int r = 0; r < kTT; ++r) { pos[r] = 0.f; prod[r] = 1.f; }
+#pragma unroll
+      for (int i = 0; i < NCI; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = i + 1 < NCI || c < C;
+#pragma unroll
+        for (int r = 0; r < kTT; ++r) {
+          const float xv = v[i][r];
+          xs[r * Cp + c] = xv;
+          const float f = 1.f + stream::ex2f(-fabsf(xv) * stream::kLog2e);
+          pos[r] += in ? fmaxf(xv, 0.f) : 0.f;
+          prod[r] *= in ? f : 1.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kTT; ++r) sp[r] = fmaf(lg2f_fast(prod[r]), 0.6931471805599453f, pos[r]);
+    }
+    warp_sum4(sp, lane);
+    __syncwarp();
+    float d[kTT];
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) d[r] = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) {
+      if (wi < words) {
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int kk = wi * 4 + bb;
+          if (kk == 0) continue;  // byte 0 is the count
+          if (kk <= n) {
+            const float* col = xs + ((lw[wi] >> (8 * bb)) & 0xffu);
+#pragma unroll
+            for (int r = 0; r < kTT; ++r) d[r] += col[r * Cp];
+          }
+        }
+      }
+    }
+    float pe[kTT][1];
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) pe[r][0] = valid ? fmaxf(stream::ex2f((d[r] - sp[r]) * k2), stream::kPMin) : 0.f;
+    if (want_grad && estore) {
+      float* e0 = e_b + (int64_t)k * kTT * estride;
+#pragma unroll
+      for (int r = 0; r < kTT; ++r)
+        if (r < nrow) e0[r * estride] = pe[r][0];
+    }
+    __syncwarp();  // the staged rows are free for the next tile
+    if (k > 0) {
+      if ((k & 1) == 0) {
+        lane_rescale<1, true>(x, e, fac, lane);
+        if (want_grad && valid) cke[(k >> 1) * 32] = e;
+      }
+      if (want_grad && valid) ckx[k * 32] = x[0];
+    }
+#pragma unroll
+    for (int r = 0; r < kTT; ++r)
+      if (r < nrow) alpha_step<1>(x, pe[r], fac);
+  }
+  // ---- read-out (NoBlankBinaryCTC.py:58-68)
+  double zinv;
+  int Ez;
+  {
+    double zhat = __shfl_sync(kFull, x[0], Lb - 1);
+    Ez = __shfl_sync(kFull, e, Lb - 1);
+    const int ezf = __double2hiint(zhat) >> 20;
+    const bool ok = zhat > 0.0 && ezf > 0 && ezf < 0x7ff;
+    if (ok) {
+      zhat *= pow2z(1023 - ezf);
+      Ez += ezf - 1023;
+    }
+    if (lane == 0) p.loss[b] = ok ? (float)(-(log(zhat) + (double)Ez * 0.6931471805599453)) : INFINITY;
+    zinv = ok ? 1.0 / zhat : 0.0;
+    if (!ok) return;  // K3 writes zero rows for a sequence without a finite loss
+  }
+  if (!want_grad) return;
+  __syncwarp();
+
+  // ================================================================ phase 2: gamma over p in the tile
+  double u[1] = {lane < Lb ? (((Lb - 1 - lane) & 1) ? -1.0 : 1.0) : 0.0};
+  int eb = 0;
+  double facb = lane == 31 ? 0.0 : 1.0;
+  int since = 0;
+  for (int k = K - 1; k >= 0; --k) {
+    const int nrow = min(kTT, Tb - k * kTT);
+    float* e0 = e_b + (int64_t)k * kTT * estride;
+    float pe[kTT][1];
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) pe[r][0] = (r < nrow && estore) ? e0[r * estride] : 0.f;
+    double xa[1];
+    int ea = 0;
+    if (k == 0) {
+      xa[0] = (lane & 1) ? -1.0 : 1.0;
+    } else {
+      xa[0] = valid ? ckx[k * 32] : 0.0;
+      if (k >= 2 && valid) ea = cke[(k >> 1) * 32];
+    }
+    const int H = ea + eb - Ez;
+    const int Ha = max(min(H, 0), -1000);
+    const double ga = pow2z(Ha), gb = pow2z(H - Ha) * zinv;
+    const int eu = __shfl_up_sync(kFull, ea, 1);
+    const double faca = lane == 0 ? 0.0 : pow2z(eu - ea);
+    double a[kTT];
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) {
+      if (r < nrow) alpha_step<1>(xa, pe[r], faca);
+      a[r] = xa[0] * ga;
+    }
+#pragma unroll
+    for (int r = kTT - 1; r >= 0; --r) {
+      if (r < nrow) {
+        double bt[1];
+        beta_step<1>(u, bt, pe[r], facb);
+        const float g = (float)(a[r] * clamp_big(bt[0] * gb));
+        if (estore) e0[r * estride] = g;
+      }
+    }
+    if (++since == 2 || nrow < kTT) {
+      since = 0;
+      lane_rescale<1, false>(u, eb, facb, lane);
+    }
+  }
+}
+
+template <int NCI>
+int launch_bin_seq(const Problem& p, const TiledWs& w, cudaStream_t stream) {
+  bin_seq_kernel<NCI><<<(unsigned)p.B, 32, 0, stream>>>(p, w);
+  NBCTC_LAUNCH_CHECK();
+  return NBCTC_OK;
 }
 
 // ------------------------------------------------------------------------------------ K2: lattice on emission tiles
@@ -709,12 +952,28 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   w.cke = reinterpret_cast<int*>(c + l.o_cke);
   w.emis = reinterpret_cast<float*>(c + l.o_emis);
   w.LW = l.LW; w.NT = l.NT; w.Lpad = l.Lpad;
+  w.rec = c + l.o_rec; w.rec_bytes = (int64_t)l.rec_bytes; w.o_rec_ckx = l.o_rec_ckx;
   *flag_out = w.flag;
   // the flag and the class masks (set with atomicOr by the emission kernel) are contiguous: one memset
   NBCTC_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, l.o_cmask + sizeof(uint32_t) * (size_t)p.B * p.C * l.LW, stream));
   const dim3 grid((unsigned)p.B, (unsigned)((p.T + kTCh - 1) / kTCh));
   int rc;
   const int nci = (int)((p.C + 31) / 32);
+  static const bool no_seq = getenv("NBCTC_BIN_NOSEQ") != nullptr;
+  if (l.seq && !no_seq) {  // emissions + lattice in one sequence-per-warp kernel
+    switch (nci) {
+      case 1: rc = launch_bin_seq<1>(p, w, stream); break;
+      case 2: rc = launch_bin_seq<2>(p, w, stream); break;
+      case 3: rc = launch_bin_seq<3>(p, w, stream); break;
+      case 4: rc = launch_bin_seq<4>(p, w, stream); break;
+      case 5: rc = launch_bin_seq<5>(p, w, stream); break;
+      case 6: rc = launch_bin_seq<6>(p, w, stream); break;
+      case 7: rc = launch_bin_seq<7>(p, w, stream); break;
+      default: rc = launch_bin_seq<8>(p, w, stream); break;
+    }
+    if (rc != NBCTC_OK || p.grad == nullptr) return rc;
+    goto gradient;
+  }
   switch (nci) {
     case 1: rc = launch_emis<1>(p, w, grid, stream); break;
     case 2: rc = launch_emis<2>(p, w, grid, stream); break;
@@ -734,6 +993,7 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   }
   if (rc != NBCTC_OK || p.grad == nullptr) return rc;
 
+gradient:
   switch (nci) {
     case 1: return launch_grad<1>(p, w, grid, stream);
     case 2: return launch_grad<2>(p, w, grid, stream);
