@@ -14,6 +14,9 @@
 //                      16 lanes x NS states per direction, exact power-of-two rescaling, one alpha checkpoint per
 //                      tile of 8 steps, alpha replay next to beta in phase 2) on the emission tiles;
 //                      gamma overwrites the emissions (NoBlankBinaryCTC.py:72-95 transition, read-out :58-68).
+//   K12 bin_seq      : Lmax <= 32 (BASELINE configs[2]): K1 and K2 as ONE sequence-per-warp kernel (the scheme of
+//                      seqwarp_kernel.cuh: warp = sequence, tiles of 4 steps, float64 chain on all 32 lanes with
+//                      per-lane scales, alpha replay from a checkpoint per tile) -- see its comment below.
 //   K3 bin_grad      : CTA = one sequence x 256 time steps, 16 warps, warp = batches of 4 rows staged by TMA bulk
 //                      copies (double buffered), lane = class: grad = w/C * (sigmoid(x) - sum_{s in M_c} gamma_t(s)),
 //                      the states of a class decoded once per CTA into a round table (ascending state order:
@@ -316,6 +319,11 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   double fac = lane == 0 ? 0.0 : 1.0;
   const int K = (Tb + kTT - 1) / kTT;
   const float* xr = p.logits + b * p.C + lane;  // row t = 0
+  // one prefetch.global.L1 per tile requests the next tile's rows: lane = (row of the tile, 128-byte line of the row)
+  const int LW = min((C * 4 + 127) / 128 + 1, 8);
+  const int pf_ri = lane / LW;
+  const int pf_d = pf_ri * (int)rstride * 4 + min((lane - pf_ri * LW) * 128, C * 4 - 4) - 4 * lane;
+  const bool pf_lane = lane < kTT * LW;
   for (int k = 0; k < K; ++k) {
     const int nrow = min(kTT, Tb - k * kTT);
     float v[NCI][kTT];
@@ -325,6 +333,7 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
       for (int i = 0; i < NCI; ++i) v[i][r] = ((i + 1 < NCI || lane + 32 * i < C) && r < nrow) ? ldg_f(xr + 32 * i) : 0.f;
       xr += rstride;
     }
+    if (pf_lane && (k + 1) * kTT + pf_ri < Tb) pf_line_l1(reinterpret_cast<const char*>(xr) + pf_d);
     // sum_c softplus(x_c) = sum_c max(x_c, 0) + log prod_c (1 + exp(-|x_c|))  (K1)
     float sp[kTT];
     {
@@ -412,20 +421,33 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   int eb = 0;
   double facb = lane == 31 ? 0.0 : 1.0;
   int since = 0;
+  // the tile's emissions, checkpoint and lane scale are loaded one tile ahead of their use
+  float pe_n[kTT];
+  double xa_n;
+  int ea_n;
+  auto fetch = [&](int k) {
+    const int nrow = min(kTT, Tb - k * kTT);
+    const float* e0 = e_b + (int64_t)k * kTT * estride;
+#pragma unroll
+    for (int r = 0; r < kTT; ++r) pe_n[r] = (r < nrow && estore) ? e0[r * estride] : 0.f;
+    ea_n = 0;
+    if (k == 0) {
+      xa_n = (lane & 1) ? -1.0 : 1.0;
+    } else {
+      xa_n = valid ? ckx[k * 32] : 0.0;
+      if (k >= 2 && valid) ea_n = cke[(k >> 1) * 32];
+    }
+  };
+  fetch(K - 1);
   for (int k = K - 1; k >= 0; --k) {
     const int nrow = min(kTT, Tb - k * kTT);
     float* e0 = e_b + (int64_t)k * kTT * estride;
     float pe[kTT][1];
 #pragma unroll
-    for (int r = 0; r < kTT; ++r) pe[r][0] = (r < nrow && estore) ? e0[r * estride] : 0.f;
-    double xa[1];
-    int ea = 0;
-    if (k == 0) {
-      xa[0] = (lane & 1) ? -1.0 : 1.0;
-    } else {
-      xa[0] = valid ? ckx[k * 32] : 0.0;
-      if (k >= 2 && valid) ea = cke[(k >> 1) * 32];
-    }
+    for (int r = 0; r < kTT; ++r) pe[r][0] = pe_n[r];
+    double xa[1] = {xa_n};
+    const int ea = ea_n;
+    if (k > 0) fetch(k - 1);
     const int H = ea + eb - Ez;
     const int Ha = max(min(H, 0), -1000);
     const double ga = pow2z(Ha), gb = pow2z(H - Ha) * zinv;
