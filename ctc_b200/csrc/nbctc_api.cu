@@ -91,6 +91,10 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
         float* row_lse_out = nullptr) {
   if (flags & NBCTC_FLAG_NO_GRAD) p.grad = nullptr;
   p.sum_weighted = (flags & NBCTC_FLAG_SUM_WEIGHTED) != 0;
+  if (ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return NBCTC_ERR_INVALID_ARG;
+  }
   int rc;
   bool use_sw = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_seqwarp(flags, p.T, p.B, p.C, p.Lmax);
   // the wide-row variant moves rows with TMA: 16-byte aligned tensors only (else the paths below)

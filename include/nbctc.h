@@ -71,8 +71,9 @@ int nbctc_version(void);
 /* Last error message of the calling thread ("" if none). Never NULL. */
 const char* nbctc_last_error(void);
 
-/* Bytes of scratch the caller must provide for one call with these shapes.
- * `binary` = 0 for nbctc_*, 1 for nbbctc_*.  Returns 0 on invalid shapes. */
+/* Bytes of scratch the caller must provide for one call with these shapes (same `flags` as the call).
+ * `binary` = 0 for nbctc_*, 1 for nbbctc_*.  Returns 0 on invalid shapes.  The workspace pointer handed to the loss
+ * calls must be 256-byte aligned (cudaMalloc and torch allocations are); NBCTC_ERR_INVALID_ARG otherwise. */
 size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int binary, uint32_t flags);
 
 /*

@@ -154,3 +154,50 @@ def test_default_dispatch_takes_the_seqwarp_kernel_for_large_batches():
     torch.cuda.synchronize()
     assert np.array_equal(per.detach().cpu().double().numpy(), per_f)
     assert np.array_equal(xt.grad.cpu().double().numpy(), g_f)
+
+
+@pytest.mark.parametrize("shape", [(37, 9, 157, 20), (23, 5, 33, 33), (19, 4, 260, 9), (30, 3, 1000, 200), (40, 1500, 12, 5)],
+                         ids=lambda s: "T%d_B%d_C%d_L%d" % s)
+def test_no_write_outside_the_caller_buffers(shape):
+    """Gradient, per-sequence losses and workspace sit between guard regions of a known byte pattern: the kernels write
+    every byte of the gradient and nothing outside what nbctc_workspace_bytes() asked for."""
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    T, B, C, Lmax = shape
+    x, lab, il, tl = make_ctc_case(500 + T + C, T, B, C, Lmax)
+    xt = torch.tensor(x, device=DEV)
+    labt = torch.tensor(lab, device=DEV).int().contiguous()
+    ilt, tlt = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    flags = SEQWARP | _ffi.FLAG_ALIGNED16
+    wsb = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 0, flags))
+    G = 4096                                              # guard bytes (keeps every buffer 256-byte aligned)
+    up = lambda n: (n + 255) // 256 * 256
+    n_grad, n_per, n_ws = up(T * B * C * 4), up(B * 4), up(wsb)
+    arena = torch.full((G + n_grad + G + n_per + G + n_ws + G,), 0x5A, dtype=torch.uint8, device=DEV)
+    o_grad, o_per, o_ws = G, G + n_grad + G, G + n_grad + G + n_per + G
+    base = arena.data_ptr()
+    assert base % 256 == 0
+    rc = lib.nbctc_loss_grad_f32(xt.data_ptr(), T, B, C, labt.data_ptr(), Lmax, ilt.data_ptr(), tlt.data_ptr(), base + o_per, None, None,
+                                 base + o_grad, None, 1.0, base + o_ws, wsb, flags, torch.cuda.current_stream().cuda_stream)
+    _ffi.check(rc, "nbctc_loss_grad_f32")
+    torch.cuda.synchronize()
+    a = arena.cpu().numpy()
+    for lo, hi in ((0, G), (o_grad + T * B * C * 4, o_per), (o_per + B * 4, o_ws), (o_ws + wsb, len(a))):
+        assert np.all(a[lo:hi] == 0x5A), f"guard bytes [{lo},{hi}) were written"
+    grad = a[o_grad:o_grad + T * B * C * 4].view(np.float32).reshape(T, B, C).astype(np.float64)
+    per = a[o_per:o_per + B * 4].view(np.float32).astype(np.float64)
+    _check(per, grad, x, lab, il, tl)
+
+
+def test_misaligned_workspace_is_rejected():
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    x, lab, il, tl = make_ctc_case(1, 8, 2, 16, 3)
+    xt, labt = torch.tensor(x, device=DEV), torch.tensor(lab, device=DEV).int()
+    ilt, tlt = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    per, grad = torch.empty(2, device=DEV), torch.empty_like(xt)
+    wsb = int(lib.nbctc_workspace_bytes(8, 2, 16, 3, 0, 0))
+    ws = torch.empty(wsb + 512, dtype=torch.uint8, device=DEV)
+    rc = lib.nbctc_loss_grad_f32(xt.data_ptr(), 8, 2, 16, labt.data_ptr(), 3, ilt.data_ptr(), tlt.data_ptr(), per.data_ptr(), None, None,
+                                 grad.data_ptr(), None, 1.0, ws.data_ptr() + 16, wsb, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"aligned" in lib.nbctc_last_error()
