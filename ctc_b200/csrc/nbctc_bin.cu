@@ -524,7 +524,13 @@ __device__ __forceinline__ void lat_phase2_regs(double (&x)[NS], stream::ChainSc
     const int eu = __shfl_up_sync(0xffffffffu, c.e, 1, W);
     if (!isb) c.fac = hl == 0 ? 0.0 : pow2z(eu - c.e);
   }
-  const double bs = isb ? pow2z(c.e + (k == 0 ? 0 : eck) - c.Ez) * c.zinv : 1.0;
+  // beta entry = beta * 2^H / Zhat, H = e_beta + e_alpha - E_z.  H can fall below the float64 exponent range while the
+  // product with the alpha entry is of order one (alpha and beta both large in their lanes' scales: mass that has just
+  // arrived through lanes scaled for it -- every state of a sequence with a single admissible path and emissions near
+  // one), so the power of two is applied in two exact steps
+  const int Hs = isb ? c.e + (k == 0 ? 0 : eck) - c.Ez : 0;
+  const double bs = isb ? pow2z(max(Hs, -1000)) * c.zinv : 1.0;
+  const double bs2 = pow2z(min(Hs + 1000, 0));
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
   const int sdir = isb ? -1 : 1;
   double* dst = abt + (isb ? TT * AS : 0) + s0;
@@ -534,7 +540,7 @@ __device__ __forceinline__ void lat_phase2_regs(double (&x)[NS], stream::ChainSc
     if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry, c.fac);
     else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0, c.fac);
 #pragma unroll
-    for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
+    for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) * bs2 : x[j];
   }
   c.carry = 0.0;
   int e2 = c.e;

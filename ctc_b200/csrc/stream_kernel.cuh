@@ -428,7 +428,13 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
     const int eu = __shfl_up_sync(0xffffffffu, c.e, 1, W);
     if (!isb) c.fac = hl == 0 ? 0.0 : pow2z(eu - c.e);
   }
-  const double bs = isb ? pow2z(c.e + (k == 0 ? 0 : eck) - c.Ez) * c.zinv : 1.0;
+  // beta entry = beta * 2^H / Zhat, H = e_beta + e_alpha - E_z.  H can fall below the float64 exponent range while the
+  // product with the alpha entry is of order one (alpha and beta both large in their lanes' scales: mass that has just
+  // arrived through lanes scaled for it -- every state of a sequence with a single admissible path and emissions near
+  // one), so the power of two is applied in two exact steps
+  const int Hs = isb ? c.e + (k == 0 ? 0 : eck) - c.Ez : 0;
+  const double bs = isb ? pow2z(max(Hs, -1000)) * c.zinv : 1.0;
+  const double bs2 = pow2z(min(Hs + 1000, 0));
   const int nv = min(TT, Tb - k * TT);
   // position -> state index of this lane's slots
   const int s0 = isb ? (Lpad - 1 - hl * NS) : hl * NS;
@@ -444,7 +450,7 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
       if (jj == 0) chain_step<NS, W, true, true>(x, sum, pr[jj], hl, c.carry, c.fac);
       else chain_step<NS, W, true, false>(x, sum, pr[jj], hl, 0.0, c.fac);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
+      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) * bs2 : x[j];
     }
   } else {
 #pragma unroll 2
@@ -454,7 +460,7 @@ __device__ __forceinline__ void chain_phase2(double (&x)[NS], ChainScal& c, int 
       load_p<NS, W>(pt + i * PS, hl, isb, pf);
       chain_step_rt<NS, W, true>(x, sum, pf, hl, c.carry, c.fac, jj == 0);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) : x[j];
+      for (int j = 0; j < NS; ++j) dst[i * AS + sdir * j] = isb ? fmin(sum[j] * bs, 1e300) * bs2 : x[j];
     }
   }
   c.carry = 0.0;

@@ -496,3 +496,65 @@ def test_repeated_labels_are_bit_reproducible(nb, flags):
     l2, g2 = run_cuda(nb, "ctc", x, lab, il, tl, flags=flags)
     assert np.array_equal(l1, l2) and np.array_equal(g1, g2)
     assert_parity(l1, g1, oracle("ctc", x, lab, il, tl))
+
+
+SINGLE_PATH = [
+    # Lmax, target lengths (all but the last sequence have T_b == L_b: one admissible path, gamma one-hot, and alpha AND
+    # beta of every state on the path are "mass that has just arrived" in their lanes' scales)
+    (32, [5, 17, 23, 32, 20]), (40, [5, 17, 23, 33, 40, 20]), (64, [40, 50, 64, 30]), (100, [70, 100, 35, 50]),
+    (256, [130, 200, 256, 100]),
+]
+
+
+def _single_path_case(kind, Lmax, Ls, boost, seed=0):
+    rs = np.random.RandomState(seed + Lmax)
+    B, T = len(Ls), max(Ls)
+    C = 100 if kind == "bctc" else 64
+    x = rs.standard_normal((T, B, C)).astype(np.float32)
+    tl = np.array(Ls, dtype=np.int64)
+    il = tl.copy()
+    il[-1] = T
+    if kind == "bctc":
+        y = (rs.uniform(size=(B, Lmax, C)) < 0.05).astype(np.float32)
+        y[np.arange(B)[:, None], np.arange(Lmax)[None, :], rs.randint(0, C, size=(B, Lmax))] = 1.0
+        for b in range(B):
+            y[b, tl[b]:] = 0.0
+        return x, y, il, tl
+    lab = rs.randint(0, C, size=(B, Lmax)).astype(np.int32)
+    for b in range(B):
+        lab[b, tl[b]:] = -1
+        if boost and il[b] == tl[b]:
+            x[np.arange(tl[b]), b, lab[b, :tl[b]]] += boost   # emissions near one along the forced path
+    return x, lab, il, tl
+
+
+@pytest.mark.parametrize("boost", [0.0, 15.0], ids=["plain", "peaked_on_path"])
+@pytest.mark.parametrize("flags", [1, 8, 16, 32], ids=["generic", "lockstep", "pipeline", "seqwarp"])
+@pytest.mark.parametrize("case", SINGLE_PATH, ids=lambda c: "L%d" % c[0])
+def test_single_admissible_path_ctc(nb, case, flags, boost):
+    Lmax, Ls = case
+    x, lab, il, tl = _single_path_case("ctc", Lmax, Ls, boost)
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl, reduction="sum", flags=flags)
+    ref = oracle("ctc", x, lab, il, tl, "sum")
+    assert_parity(loss, grad, ref, scale=1e-3)
+    # every sequence on its own (a wrong short sequence hides in the batch norm).  With emissions near one the gradient
+    # of a forced path is 1 - p ~ 2e-5 itself, below what a float32 softmax resolves to 1e-5 relative: absolute bar there
+    for b in range(len(Ls) - 1):
+        if boost:
+            assert np.max(np.abs(grad[:, b] - ref["grad"][:, b])) < 2e-6      # a few float32 ulps of the O(1) terms w p and gamma
+        else:
+            assert rel_l2(grad[:, b], ref["grad"][:, b]) < 1e-5
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+@pytest.mark.parametrize("case", SINGLE_PATH, ids=lambda c: "L%d" % c[0])
+def test_single_admissible_path_bctc(nb, case, flags):
+    """Found in round 2: emissions of the multi-label variant are near one, so alpha and beta stay large in their lanes'
+    scales along a forced path and the single power-of-two factor of the beta entries underflowed (gamma = 0)."""
+    Lmax, Ls = case
+    x, y, il, tl = _single_path_case("bctc", Lmax, Ls, 0.0)
+    loss, grad = run_cuda(nb, "bctc", x, y, il, tl, reduction="sum", flags=flags)
+    ref = oracle("bctc", x, y, il, tl, "sum")
+    assert_parity(loss, grad, ref)
+    for b in range(len(Ls)):
+        assert rel_l2(grad[:, b], ref["grad"][:, b]) < 1e-5

@@ -201,3 +201,35 @@ def test_misaligned_workspace_is_rejected():
     rc = lib.nbctc_loss_grad_f32(xt.data_ptr(), 8, 2, 16, labt.data_ptr(), 3, ilt.data_ptr(), tlt.data_ptr(), per.data_ptr(), None, None,
                                  grad.data_ptr(), None, 1.0, ws.data_ptr() + 16, wsb, 0, torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"aligned" in lib.nbctc_last_error()
+
+
+@pytest.mark.parametrize("shape", [(37, 9, 157, 20), (41, 6, 40, 32), (26, 5, 100, 50)], ids=lambda s: "T%d_B%d_C%d_L%d" % s)
+def test_multilabel_no_write_outside_the_caller_buffers(shape):
+    """The same guard-region check for the multi-label variant (Lmax <= 32: the fused emission + lattice kernel)."""
+    from ctc_b200 import _ffi
+    from helpers import make_bctc_case
+    lib = _ffi.lib()
+    T, B, C, Lmax = shape
+    x, y, il, tl = make_bctc_case(600 + T, T, B, C, Lmax)
+    xt, yt = torch.tensor(x, device=DEV), torch.tensor(y, device=DEV).float().contiguous()
+    ilt, tlt = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    flags = _ffi.FLAG_ALIGNED16
+    wsb = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 1, flags))
+    G = 4096
+    up = lambda n: (n + 255) // 256 * 256
+    n_grad, n_per, n_ws = up(T * B * C * 4), up(B * 4), up(wsb)
+    arena = torch.full((G + n_grad + G + n_per + G + n_ws + G,), 0x5A, dtype=torch.uint8, device=DEV)
+    o_grad, o_per, o_ws = G, G + n_grad + G, G + n_grad + G + n_per + G
+    base = arena.data_ptr()
+    rc = lib.nbbctc_loss_grad_f32(xt.data_ptr(), T, B, C, yt.data_ptr(), Lmax, ilt.data_ptr(), tlt.data_ptr(), base + o_per, None, None,
+                                  base + o_grad, None, 1.0, base + o_ws, wsb, flags, torch.cuda.current_stream().cuda_stream)
+    _ffi.check(rc, "nbbctc_loss_grad_f32")
+    torch.cuda.synchronize()
+    a = arena.cpu().numpy()
+    for lo, hi in ((0, G), (o_grad + T * B * C * 4, o_per), (o_per + B * 4, o_ws), (o_ws + wsb, len(a))):
+        assert np.all(a[lo:hi] == 0x5A), f"guard bytes [{lo},{hi}) were written"
+    grad = a[o_grad:o_grad + T * B * C * 4].view(np.float32).reshape(T, B, C).astype(np.float64)
+    per = a[o_per:o_per + B * 4].view(np.float32).astype(np.float64)
+    ref = cport.loss_grad("bctc", x, y, il, tl, reduction="sum")
+    assert np.max(np.abs(per - ref["per_seq"]) / np.abs(ref["per_seq"])) < TOL
+    assert rel_l2(grad, ref["grad"]) < TOL
