@@ -16,7 +16,6 @@ FLAG_GENERIC = 1
 FLAG_NO_GRAD = 2
 FLAG_ALIGNED16 = 4
 FLAG_LOCKSTEP = 8
-FLAG_PIPELINE = 16
 FLAG_SEQWARP = 32
 FLAG_SUM_WEIGHTED = 64
 

@@ -71,12 +71,6 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
 bool fused_pointers_ok(const Problem& p);  // logits / grad 16-byte aligned (the bulk copies need it)
 extern long long* g_stream_prof;           // role-profiler buffer (-DNBCTC_PROF builds), else null
 
-// pipeline path of the single-label variant (nbctc_pipe.cu: persistent ticket-scheduled kernel, stage A rows ->
-// stage B chains -> stage C rows)
-bool pipe_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
-size_t pipe_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
-int pipe_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t stream);
-
 // sequence-per-warp path of the single-label variant (nbctc_seqwarp.cu: one warp per sequence, whole batch in flight)
 bool seqwarp_supported(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 bool seqwarp_is_wide(int64_t T, int64_t B, int64_t C, int64_t Lmax);  // rows through a shared-memory ring (needs 16-byte alignment)

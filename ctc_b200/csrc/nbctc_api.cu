@@ -46,20 +46,16 @@ __global__ void scale_grad_kernel(float* __restrict__ g, int64_t n_vec4, int64_t
   }
 }
 
-// which fused single-label kernel: NBCTC_FLAG_PIPELINE / NBCTC_FLAG_LOCKSTEP, else the NBCTC_PATH environment variable
-// ("pipe" | "lockstep", read once), else the lock-step kernel
-int env_path() {  // 0 none, 1 "pipe", 2 "lockstep", 3 "seqwarp"
+// which single-label kernel: NBCTC_FLAG_SEQWARP / NBCTC_FLAG_LOCKSTEP, else the NBCTC_PATH environment variable
+// ("seqwarp" | "lockstep", read once), else by batch size (want_seqwarp)
+int env_path() {  // 0 none, 2 "lockstep", 3 "seqwarp"
   static const int env = [] {
     const char* v = getenv("NBCTC_PATH");
-    return !v ? 0 : v[0] == 'p' ? 1 : v[0] == 'l' ? 2 : v[0] == 's' ? 3 : 0;
+    return !v ? 0 : v[0] == 'l' ? 2 : v[0] == 's' ? 3 : 0;
   }();
   return env;
 }
-constexpr uint32_t kPathFlags = NBCTC_FLAG_PIPELINE | NBCTC_FLAG_LOCKSTEP | NBCTC_FLAG_SEQWARP;
-bool want_pipeline(uint32_t flags) {
-  if (flags & kPathFlags) return (flags & NBCTC_FLAG_PIPELINE) != 0;
-  return env_path() == 1;
-}
+constexpr uint32_t kPathFlags = NBCTC_FLAG_LOCKSTEP | NBCTC_FLAG_SEQWARP;
 // the sequence-per-warp kernel: on request, else for batches that fill the GPU with one sequence per warp (the
 // lock-step kernel keeps the small batches: it spreads ONE sequence over a whole CTA)
 bool want_seqwarp(uint32_t flags, int64_t T, int64_t B, int64_t C, int64_t Lmax) {
@@ -115,11 +111,7 @@ int run(Problem& p, bool binary, void* ws, size_t ws_bytes, uint32_t flags, cuda
     return NBCTC_ERR_INVALID_ARG;
   }
   const bool use_fused = shape_ok && fused_pointers_ok(p);
-  const bool use_pipe = !binary && !(flags & NBCTC_FLAG_GENERIC) && want_pipeline(flags) && fused_pointers_ok(p) &&
-                        pipe_supported(p.T, p.B, p.C, p.Lmax);
-  if (use_pipe) {
-    rc = pipe_launch(p, ws, ws_bytes, stream);
-  } else if (use_fused) {
+  if (use_fused) {
     rc = fused_launch(p, binary, ws, ws_bytes, stream);
   } else if (binary && !(flags & NBCTC_FLAG_GENERIC) && tiled_bin_supported(p.T, p.B, p.C, p.Lmax) &&
              (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {  // the TMA row copies read 16-byte aligned supersets
@@ -305,7 +297,6 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
   // the generic size is kept as a floor: a call with 16-byte misaligned tensors falls back to that path
   size_t f = 0;
   if (fused_supported(T, B, C, Lmax, binary != 0)) f = fused_workspace_bytes(T, B, C, Lmax, binary != 0);
-  if (!binary && want_pipeline(flags) && pipe_supported(T, B, C, Lmax)) f = std::max(f, pipe_workspace_bytes(T, B, C, Lmax));
   if (!binary && want_seqwarp(flags, T, B, C, Lmax)) {
     const size_t sw = seqwarp_workspace_bytes(T, B, C, Lmax);
     if (!seqwarp_is_wide(T, B, C, Lmax)) return sw;  // any alignment

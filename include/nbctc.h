@@ -49,11 +49,9 @@ extern "C" {
                                      then omits the room for the unaligned-tensor fallback (the call fails with
                                      NBCTC_ERR_INVALID_ARG if the promise is broken) */
 
-#define NBCTC_FLAG_LOCKSTEP 8u    /* single-label variant: the lock-step fused kernel (the default; stream_kernel.cuh) */
-#define NBCTC_FLAG_PIPELINE 16u   /* single-label variant: the pipeline kernel (pipe_kernel.cuh: ticket-scheduled row and
-                                     chain stages).  Without either flag the NBCTC_PATH environment variable
-                                     ("pipe" / "lockstep") decides, else the lock-step kernel */
-
+#define NBCTC_FLAG_LOCKSTEP 8u    /* single-label variant: the lock-step fused kernel (stream_kernel.cuh; the default for small
+                                     batches).  Without a path flag the NBCTC_PATH environment variable ("seqwarp" /
+                                     "lockstep") decides, else the batch size.  (16u was round 2's pipeline kernel: removed) */
 #define NBCTC_FLAG_SEQWARP 32u    /* single-label variant: the sequence-per-warp kernels (seqwarp_kernel.cuh: C <= 256, Lmax <= 64;
                                      seqwide_kernel.cuh: C % 4 == 0, C <= 1024, Lmax <= 256, 16-byte aligned tensors).
                                      Without a path flag they take the batches that fill the GPU with one sequence per

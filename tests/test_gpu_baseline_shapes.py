@@ -56,7 +56,7 @@ def check_subset(per, grad_sub, x_sub, tg_sub, il_sub, tl_sub, B_total, kind="ct
     return rl, rg, linf
 
 
-@pytest.mark.parametrize("flags", [0, 8, 16, 32], ids=["default", "lockstep", "pipeline", "seqwarp"])
+@pytest.mark.parametrize("flags", [0, 8, 32], ids=["default", "lockstep", "seqwarp"])
 @pytest.mark.parametrize("ragged", [False, True], ids=["fixedT", "raggedT"])
 def test_cfg2_full_batch(nb, ragged, flags):
     """BASELINE configs[1]: B=4096, T=256, C=157, ragged L in [1,32]; every sequence against the oracle."""
@@ -122,13 +122,13 @@ def _big_case(nb, T, B, C, Lmax, seed, n_sub, flags=0):
     return check_subset(per.detach()[subd].cpu().double().numpy(), g_sub, x_sub, lab[sub], il[sub], tl[sub], B)
 
 
-@pytest.mark.parametrize("flags", [0, 8, 16], ids=["default", "lockstep", "pipeline"])
+@pytest.mark.parametrize("flags", [0, 8], ids=["default", "lockstep"])
 def test_cfg4_full_size_subset(nb, flags):
     """BASELINE configs[3]: B=1024, T=4096, C=1024, L<=256, ragged input_length (16 states per chain lane)."""
     _big_case(nb, 4096, 1024, 1024, 256, seed=40, n_sub=64, flags=flags)
 
 
-@pytest.mark.parametrize("flags", [0, 8, 16], ids=["default", "lockstep", "pipeline"])
+@pytest.mark.parametrize("flags", [0, 8], ids=["default", "lockstep"])
 def test_cfg5_shard_full_size_subset(nb, flags):
     """BASELINE configs[4] shard at 8 GPUs: B=8192, T=512, C=157, L<=64, ragged input_length."""
     _big_case(nb, 512, 8192, 157, 64, seed=50, n_sub=96, flags=flags)
@@ -146,7 +146,7 @@ PEAKED = [
 ]
 
 
-@pytest.mark.parametrize("flags", [0, 1, 16, 32], ids=["default", "generic", "pipeline", "seqwarp"])
+@pytest.mark.parametrize("flags", [0, 1, 8, 32], ids=["default", "generic", "lockstep", "seqwarp"])
 @pytest.mark.parametrize("case", PEAKED, ids=lambda c: "T%d_B%d_C%d_L%d_%d_boost%g_s%d" % c)
 def test_peaked_logits(nb, case, flags):
     """A model that is confident in one class for the whole sequence: the lattice states differ by thousands of binary

@@ -1,6 +1,6 @@
-"""Development check of the pipeline kernel against the CPU oracle port on a few shapes (GPU box).
+"""Development check of one single-label kernel against the CPU oracle port on a few shapes (GPU box).
 
-    [NBCTC_PIPE_SPLIT=1] python tools/pipe_check.py [quick|full]
+    python tools/kernel_check.py [quick|full] [seqwarp|lockstep]
 """
 import os
 import sys
@@ -15,7 +15,7 @@ from ctc_b200 import _ffi  # noqa: E402
 from oracle import cport  # noqa: E402
 
 
-DEFAULT_FLAGS = _ffi.FLAG_PIPELINE
+DEFAULT_FLAGS = _ffi.FLAG_SEQWARP
 
 
 def case(seed, T, B, C, Lmax, ragged=True, boost=0.0, dup=False, Lmin=1):
@@ -72,7 +72,7 @@ def main():
         DEFAULT_FLAGS = _ffi.FLAG_LOCKSTEP
     if len(sys.argv) > 2 and sys.argv[2] == "seqwarp":
         DEFAULT_FLAGS = _ffi.FLAG_SEQWARP
-    print("sequence-per-warp kernel;" if DEFAULT_FLAGS == _ffi.FLAG_SEQWARP else "lock-step kernel;" if DEFAULT_FLAGS == _ffi.FLAG_LOCKSTEP else "split pipeline kernel;" if os.environ.get("NBCTC_PIPE_SPLIT") else "fused pipeline kernel;", torch.cuda.get_device_name(0), flush=True)
+    print("sequence-per-warp kernel;" if DEFAULT_FLAGS == _ffi.FLAG_SEQWARP else "lock-step kernel;", torch.cuda.get_device_name(0), flush=True)
     ok = True
     ok &= run("tiny T=4 B=2", *case(0, 4, 2, 157, 3, ragged=False))
     ok &= run("cfg1-like", *case(1, 64, 8, 157, 8, ragged=False))

@@ -1,6 +1,6 @@
 """Kernel time of one path on a bench workload (CUDA events, C ABI, device-resident inputs).
 
-    python tools/time_paths.py cfg2|cfg5|cfg2r [seqwarp|lockstep|pipe] [reps]
+    python tools/time_paths.py cfg2|cfg5|cfg2r [seqwarp|lockstep|generic] [reps]
 """
 import os
 import sys
@@ -22,7 +22,7 @@ def main():
     path = sys.argv[2] if len(sys.argv) > 2 else "seqwarp"
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     T, B, C, Lmax, ragged = SHAPES[name]
-    flags = {"seqwarp": _ffi.FLAG_SEQWARP, "lockstep": _ffi.FLAG_LOCKSTEP, "pipe": _ffi.FLAG_PIPELINE}[path] | _ffi.FLAG_ALIGNED16
+    flags = {"seqwarp": _ffi.FLAG_SEQWARP, "lockstep": _ffi.FLAG_LOCKSTEP, "generic": _ffi.FLAG_GENERIC}[path] | _ffi.FLAG_ALIGNED16
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1)
     x = torch.randn(T, B, C, device=dev, generator=g)
