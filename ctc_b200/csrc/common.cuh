@@ -77,6 +77,20 @@ bool seqwarp_is_wide(int64_t T, int64_t B, int64_t C, int64_t Lmax);  // rows th
 size_t seqwarp_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax);
 int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row_lse_in, float* row_lse_out, cudaStream_t stream);
 
+// log-domain repair of the sequences whose emissions the fast single-label kernels had to floor (nbctc_logdom.cu):
+// flag[b] != 0 -> the sequence is redone; lse / ckx = scratch of the sequence (row log-partitions [T] float32, alpha
+// checkpoints [ceil(T/4)][Lpad] float64, Lpad = 32/64/128/256 by Lmax), strides in elements
+struct LogWs {
+  const int* flag;       // sequence b: flag_words (1 or 32, 16-byte aligned) ints at flag + b flag_stride, any non-zero = redo
+  int64_t flag_stride;
+  int flag_words;
+  float* lse_base;
+  int64_t lse_stride;
+  double* ckx_base;
+  int64_t ckx_stride;
+};
+int logdom_repair_launch(const Problem& p, const LogWs& w, cudaStream_t stream);
+
 // auxiliary cross-entropy on one frame per sequence, added into the gradient rows (nbctc_auxce.cu)
 int aux_ce_launch(const float* logits, int64_t T, int64_t B, int64_t C, const int64_t* frame_index, const int64_t* in_len,
                   const int32_t* y_index, const float* y_multihot, int mode, float alpha_w, const float* seq_w, float* ce_per_seq,

@@ -54,7 +54,7 @@ struct SwPlan {
   int NS, EPL, K, Tp;
   int NV, D;        // wide: float4 chunks per lane, ring slots per warp
   uint32_t o_gam, o_nxt, o_ring, smem_bytes;
-  size_t o_order, o_lse, o_ckx, o_cke, bytes;
+  size_t o_order, o_flag, o_lse, o_ckx, o_cke, bytes;
 };
 
 constexpr size_t kWideSmemBudget = 31 * 1024;  // per warp-CTA: 7 of them (+1 KB each of driver reserve) share an SM
@@ -87,6 +87,8 @@ SwPlan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   pl.Tp = pl.K * 4;
   size_t off = 256;
   pl.o_order = off;
+  off = align_up(off + sizeof(int) * (size_t)B, 256);
+  pl.o_flag = off;  // [B] sequences for the log-domain repair kernel
   off = align_up(off + sizeof(int) * (size_t)B, 256);
   pl.o_lse = off;
   if (pl.wide) {
@@ -152,6 +154,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
     W.K = pl.K;
     W.Tp = pl.Tp;
     W.D = pl.D;
+    W.floor_flag = reinterpret_cast<int*>(w + pl.o_flag);
     W.o_gam = pl.o_gam; W.o_nxt = pl.o_nxt; W.o_ring = pl.o_ring; W.smem_bytes = pl.smem_bytes;
     const int64_t resident = (int64_t)(pl.NS >= 8 ? 7 : 8) * g_sms;
     int grid;
@@ -164,7 +167,10 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
       seqwarp_prep_kernel<<<1, kPrepThreads, 0, stream>>>(p.in_len, (int)p.B, (int)p.T, const_cast<int*>(W.order), W.ticket);
       NBCTC_LAUNCH_CHECK();
     }
-    return pl.NV == 4 ? launch_seqwide_nv<4>(W, pl.NS, grid, stream) : launch_seqwide_nv<8>(W, pl.NS, grid, stream);
+    const int rcw = pl.NV == 4 ? launch_seqwide_nv<4>(W, pl.NS, grid, stream) : launch_seqwide_nv<8>(W, pl.NS, grid, stream);
+    if (rcw != NBCTC_OK) return rcw;
+    LogWs lw{W.floor_flag, 1, 1, W.lse2, (int64_t)pl.Tp, W.ckx, (int64_t)pl.K * 32 * pl.NS};
+    return logdom_repair_launch(p, lw, stream);
   }
   SwParams P{};
   P.p = p;
@@ -176,6 +182,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
     P.o_ckx = (int)align_up(P.o_cke + cke_b, 256);
     P.rec_bytes = (int64_t)align_up(P.o_ckx + sizeof(double) * (size_t)pl.K * 32 * pl.NS, 256);
   }
+  P.floor_flag = reinterpret_cast<int*>(w + pl.o_flag);
   P.row_lse_in = row_lse_in;
   P.row_lse_out = row_lse_out;
   P.K = pl.K;
@@ -193,7 +200,11 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
     seqwarp_prep_kernel<<<1, kPrepThreads, 0, stream>>>(p.in_len, (int)p.B, (int)p.T, const_cast<int*>(P.order), P.ticket);
     NBCTC_LAUNCH_CHECK();
   }
-  return launch_seqwarp(P, pl.NS, pl.EPL, grid, stream);
+  const int rcs = launch_seqwarp(P, pl.NS, pl.EPL, grid, stream);
+  if (rcs != NBCTC_OK) return rcs;
+  // sequences with an emission below the float32 floor: redone in the log domain, in their own records
+  LogWs lw{P.floor_flag, 1, 1, reinterpret_cast<float*>(P.rec), P.rec_bytes / 4, reinterpret_cast<double*>(P.rec + P.o_ckx), P.rec_bytes / 8};
+  return logdom_repair_launch(p, lw, stream);
 }
 
 int launch_seqwarp(const SwParams& P, int NS, int EPL, int grid, cudaStream_t stream) {

@@ -102,13 +102,32 @@ Plan make_plan(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   return pl;
 }
 
-size_t plan_ws_bytes(const Plan& pl, int64_t T, int64_t B) {
+// workspace: [256 | alpha checkpoints | their lane scales | repair: flags [B], row log-partitions [B][T], alpha
+// checkpoints of the log-domain repair kernel [B][ceil(T/4)][Lpad]]
+struct WsLayout {
+  size_t o_ckpt, o_cke, o_flag, o_rlse, o_rckx, total;
+  int64_t rK;
+};
+WsLayout ws_layout(const Plan& pl, int64_t T, int64_t B) {
+  WsLayout l{};
   size_t off = 256;
-  if (!pl.ok) return off;
-  (void)T;
+  l.o_ckpt = off;
   off = align_up(off + sizeof(double) * (size_t)B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
+  l.o_cke = off;
   off = align_up(off + sizeof(int) * (size_t)B * pl.cfg.NTmax * (pl.cfg.NS > 2 ? 32 : 16), 256);
-  return off;
+  l.o_flag = off;
+  off = align_up(off + sizeof(int) * (size_t)B, 256);
+  l.o_rlse = off;
+  off = align_up(off + sizeof(float) * (size_t)B * T, 256);
+  l.rK = (T + 3) / 4;
+  l.o_rckx = off;
+  off = align_up(off + sizeof(double) * (size_t)B * l.rK * pl.cfg.Lpad, 256);
+  l.total = off;
+  return l;
+}
+size_t plan_ws_bytes(const Plan& pl, int64_t T, int64_t B) {
+  if (!pl.ok) return 256;
+  return ws_layout(pl, T, B).total;
 }
 
 }  // namespace
@@ -140,25 +159,29 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
     set_error("shape or pointer alignment not supported by the fused kernel");
     return NBCTC_ERR_UNSUPPORTED;
   }
+  const WsLayout l = ws_layout(pl, p.T, p.B);
+  if (ws == nullptr || ws_bytes < l.total) {
+    set_error("workspace too small: need %zu bytes, got %zu", l.total, ws_bytes);
+    return NBCTC_ERR_WORKSPACE;
+  }
+  char* w = static_cast<char*>(ws);
   if (pl.cfg.ckpt_global) {
-    const size_t need = plan_ws_bytes(pl, p.T, p.B);
-    if (ws == nullptr || ws_bytes < need) {
-      set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
-      return NBCTC_ERR_WORKSPACE;
-    }
-    char* w = static_cast<char*>(ws);
-    size_t off = 256;
-    pl.cfg.ws_ckpt = reinterpret_cast<double*>(w + off);
-    off = align_up(off + sizeof(double) * (size_t)p.B * pl.cfg.NTmax * pl.cfg.Lpad, 256);
-    pl.cfg.ws_cke = reinterpret_cast<int*>(w + off);
+    pl.cfg.ws_ckpt = reinterpret_cast<double*>(w + l.o_ckpt);
+    pl.cfg.ws_cke = reinterpret_cast<int*>(w + l.o_cke);
   }
+  pl.cfg.floor_flag = reinterpret_cast<int*>(w + l.o_flag);
   pl.cfg.prof = g_stream_prof;
+  int rc;
   switch (pl.cfg.NS) {
-    case 2: return launch_stream_ns2(p, pl.cfg, stream);
-    case 4: return launch_stream_ns4(p, pl.cfg, stream);
-    case 8: return launch_stream_ns8(p, pl.cfg, stream);
-    default: return launch_stream_ns16(p, pl.cfg, stream);
+    case 2: rc = launch_stream_ns2(p, pl.cfg, stream); break;
+    case 4: rc = launch_stream_ns4(p, pl.cfg, stream); break;
+    case 8: rc = launch_stream_ns8(p, pl.cfg, stream); break;
+    default: rc = launch_stream_ns16(p, pl.cfg, stream); break;
   }
+  if (rc != NBCTC_OK) return rc;
+  // sequences with an emission below the float32 floor are redone in the log domain (nbctc_logdom.cu)
+  LogWs lw{pl.cfg.floor_flag, 1, 1, reinterpret_cast<float*>(w + l.o_rlse), p.T, reinterpret_cast<double*>(w + l.o_rckx), l.rK * pl.cfg.Lpad};
+  return logdom_repair_launch(p, lw, stream);
 }
 
 }  // namespace nbctc

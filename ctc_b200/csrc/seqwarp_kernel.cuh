@@ -49,6 +49,8 @@ struct SwParams {
   int* ticket;          // null: one sequence per warp (B <= warps of the grid); else the work queue
   const float* row_lse_in;  // (T,B) or null: row log-partitions supplied by the producer of the logits
   float* row_lse_out;       // (T,B) or null: row log-partitions handed to the caller
+  int* floor_flag;          // [B]: set when an emission of a live state sits on the float32 floor: the sequence is redone
+                            // in the log domain by the repair kernel (nbctc_logdom.cu), which overwrites its results
   int K;                // tiles = ceil(T / 4)
   int Tp;
 };
@@ -307,6 +309,9 @@ __device__ void Seq<NS, EPL>::run(int b) {
   }
   feas = __all_sync(kFull, feas);
   const float w = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f);
+  // slot 0 of the record's lane-scale array (scales are stored from the second rescale on) holds the lane's repair flag
+  if (lane == 0) P.floor_flag[b] = 0;
+  __syncwarp();  // ordered before the 1 any lane may store in phase 1
   if (!feas) {  // outside the parity domain: +inf, zero gradient (documented deviation)
     if (lane == 0) p.loss[b] = INFINITY;
     if (p.grad) zero_rows(p.grad, b, 0, T);
@@ -417,6 +422,19 @@ __device__ void Seq<NS, EPL>::run(int b) {
     float pe[kTT][NS];
 #pragma unroll
     for (int i = 0; i < kTT; ++i) emissions(xg[i], nl[i], act, pe[i]);
+    {  // an emission on the float32 floor: the repair kernel redoes the sequence (nothing is carried through the loop
+       // for it: the kernel sits on its register limit; the rest of this sequence's work here is simply overwritten)
+      bool low = false;
+      if (NS == 1) {  // (a lane without a state holds zeros: never equal to the floor)
+        low = fminf(fminf(pe[0][0], pe[1][0]), fminf(pe[2][0], pe[3][0])) == kPFloor;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTT; ++i)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) low |= pe[i][j] == kPFloor;
+      }
+      if (low) P.floor_flag[b] = 1;
+    }
     if (want_grad && lane == 0) *reinterpret_cast<float4*>(lse_ws + k * kTT) = make_float4(-nl[0], -nl[1], -nl[2], -nl[3]);
     if (P.row_lse_out && lane < kTT) {
       const float v = lane == 0 ? nl[0] : lane == 1 ? nl[1] : lane == 2 ? nl[2] : nl[3];
@@ -459,10 +477,15 @@ __device__ void Seq<NS, EPL>::run(int b) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) g1[j] = ldg_f(rp + goff[j]);
       emissions(g1, nl, act, pr);
+      {
+        bool low = false;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) low |= pr[j] == kPFloor;
+        if (low) P.floor_flag[b] = 1;
+      }
       alpha_step<NS>(x, pr, fac);
     }
   }
-
   // ---- read-out (NoBlankCTC.py:58-68,:139): Z = alpha_{T_b-1}(L_b-1)
   double zinv;
   int Ez;
@@ -646,6 +669,9 @@ __global__ void __launch_bounds__(kWarps * 32, NS == 1 ? 28 : NS == 2 ? 20 : 12)
   __shared__ float s_gam[kWarps][Lpad + 4];
   __shared__ unsigned short s_nxt[kWarps][Lpad + 4];
   const int lane = kWarps == 1 ? threadIdx.x : threadIdx.x & 31, wib = kWarps == 1 ? 0 : threadIdx.x >> 5;
+  // the repair kernel behind this one is launched with programmatic stream serialization: its CTAs may take their places
+  // as ours retire (they wait for this whole grid before they read a flag)
+  asm volatile("griddepcontrol.launch_dependents;");
   Seq<NS, EPL> sq(P, lane, s_gam[wib], s_nxt[wib]);
   const int B = (int)P.p.B;
   int i = blockIdx.x * kWarps + wib;

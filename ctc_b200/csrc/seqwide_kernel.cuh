@@ -30,6 +30,7 @@ struct WideParams {
   int* ticket;       // null: one sequence per warp
   int K, Tp;
   int D;             // ring slots per warp
+  int* floor_flag;   // [B] (seqwarp_kernel.cuh: SwParams::floor_flag)
   uint32_t o_gam, o_nxt, o_ring, smem_bytes;
 };
 
@@ -110,6 +111,16 @@ struct Wide {
 #pragma unroll
     for (int j = 0; j < NS; ++j) pe[j] = (actm >> j) & 1u ? fmaxf(ex2f(fmaf(r[lab[j]], kL2E, nl)), kPFloor) : 0.f;
   }
+  __device__ __forceinline__ void emissions(int slot, float nl, const int (&lab)[NS], uint32_t actm, float (&pe)[NS], bool& low) const {
+    const float* r = rowf(slot);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float raw = ex2f(fmaf(r[lab[j]], kL2E, nl));
+      const bool a = (actm >> j) & 1u;
+      low |= a && raw < kPFloor;
+      pe[j] = a ? fmaxf(raw, kPFloor) : 0.f;
+    }
+  }
   // sum of the gammas of one label in ascending state order, delivered to the label's first state
   __device__ __forceinline__ void combine(float (&g)[NS], const int (&nx1)[NS], int R) const {
     if (R > 0) {
@@ -165,6 +176,7 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
   }
   feas = __all_sync(kFull, feas);
   const float w = p.w_scalar * (p.seq_w ? p.seq_w[b] : 1.f);
+  if (lane == 0) P.floor_flag[b] = 0;
   if (!feas) {
     if (lane == 0) p.loss[b] = INFINITY;
     if (p.grad) zero_rows(b, 0, T);
@@ -216,6 +228,7 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
   for (int j = 0; j < NS; ++j) x[j] = ((lane * NS + j) & 1) ? -1.0 : 1.0;
   int e = 0;
   double fac = lane == 0 ? 0.0 : 1.0;
+  bool low = false;  // an emission below the float32 floor
   {
     const int npre = min(D, Tb);
     for (int t = 0; t < npre; ++t) issue_load(t, seq0 + (int64_t)t * strideT);
@@ -234,7 +247,7 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
         s += (ex2f(fmaf(v[i].x, kL2E, nm)) + ex2f(fmaf(v[i].y, kL2E, nm))) + (ex2f(fmaf(v[i].z, kL2E, nm)) + ex2f(fmaf(v[i].w, kL2E, nm)));
       const float nl = nm - lg2f(warp_sum1(s));
       float pe[NS];
-      emissions(slot, nl, lab, actm, pe);
+      emissions(slot, nl, lab, actm, pe, low);
       __syncwarp();  // every lane is done with the slot
       if (t + D < Tb) issue_load(slot, seq0 + (int64_t)(t + D) * strideT);
       if (want_grad && lane == 0) lse_ws[t] = -nl;
@@ -255,6 +268,10 @@ __device__ void Wide<NS, NV, FULL>::run(int b) {
       alpha_step<NS>(x, pe, fac);
       if (++slot == D) slot = 0;
     }
+  }
+  if (__any_sync(kFull, low)) {  // the log-domain repair kernel redoes this sequence
+    if (lane == 0) P.floor_flag[b] = 1;
+    return;
   }
   // ---- read-out
   double zinv;

@@ -49,6 +49,7 @@ struct StreamCfg {
   uint32_t o_bar, o_info, o_lab, o_ckpt, o_cke, o_ptile, o_s2, o_pub, o_ab, o_ring, smem_bytes;
   double* ws_ckpt;  // [B][NTmax][Lpad]
   int* ws_cke;      // [B][NTmax][W]
+  int* floor_flag;  // [B] or null: set when an emission of a live state fell below the float32 floor (nbctc_logdom.cu)
   long long* prof;  // role profiler output (NBCTC_PROF builds), else null: [3][8] buckets, then [160][32][2] trace
 };
 
@@ -730,8 +731,14 @@ struct Rows {
         const int l = label(j);
         yv[j] = yr[l >= 0 ? (l & kLabMask) : 0];
       }
+      bool low = false;
 #pragma unroll
-      for (int j = 0; j < NSL; ++j) prow[li + j * LPR] = emission(yv[j], label(j));
+      for (int j = 0; j < NSL; ++j) {
+        prow[li + j * LPR] = emission(yv[j], label(j));
+        low |= label(j) >= 0 && yv[j] * winv < kPMin;
+      }
+      // (rare) a label more than 83 nats below its row's maximum: the repair kernel redoes the sequence in the log domain
+      if (low && cfg.floor_flag != nullptr && seq < gcnt) atomicOr(&cfg.floor_flag[b0 + seq], 1);
     }
   }
 
@@ -844,6 +851,7 @@ __global__ void __launch_bounds__(Geo<NS, LPR>::NTHREADS, MINB) nbctc_stream_ker
     }
     S.info[tid] = Tb;
     S.info[kMaxGB + tid] = Lb;
+    if (tid < gcnt && cfg.floor_flag != nullptr) cfg.floor_flag[b0 + tid] = 0;  // (before the barrier: row warps may raise it)
   }
   __syncthreads();
   // duplicate ranks (the loop reads the class bits of earlier states while later ones may already be packed)

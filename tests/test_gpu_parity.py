@@ -558,3 +558,24 @@ def test_single_admissible_path_bctc(nb, case, flags):
     assert_parity(loss, grad, ref)
     for b in range(len(Ls)):
         assert rel_l2(grad[:, b], ref["grad"][:, b]) < 1e-5
+
+
+@pytest.mark.parametrize("flags", [8, 32], ids=["lockstep", "seqwarp"])
+@pytest.mark.parametrize("shape", [(64, 8, 157, 20), (50, 6, 157, 40), (40, 3, 512, 40), (70, 4, 64, 150), (33, 5, 1024, 256)],
+                         ids=lambda s: "T%d_B%d_C%d_L%d" % s)
+def test_logit_gaps_beyond_the_float32_emission_floor(nb, shape, flags):
+    """Logits whose label entries lie more than 83 nats under the row maximum: softmax(x)[label] is below 2^-120, which the
+    linear-domain kernels cannot hold.  They flag such sequences and the log-domain repair kernel redoes them; the other
+    sequences of the batch (every second one keeps N(0,1) logits) stay on the fast path."""
+    T, B, C, Lmax = shape
+    x, lab, il, tl = make_ctc_case(900 + T + C, T, B, C, Lmax)
+    x[:, 0::2] *= 40.0
+    loss, grad = run_cuda(nb, "ctc", x, lab, il, tl, reduction="none", flags=flags)
+    ref = oracle("ctc", x, lab, il, tl, "none")
+    assert np.all(np.isfinite(loss))
+    assert np.max(np.abs(loss - ref["per_seq"]) / np.abs(ref["per_seq"])) < TOL
+    for b in range(B):
+        gb, rb = grad[:, b], ref["grad"][:, b]
+        assert rel_l2(gb, rb) < TOL, f"sequence {b}"
+        assert np.max(np.abs(gb - rb)) < TOL * max(np.max(np.abs(rb)), 1e-3)
+        assert np.all(gb[il[b]:] == 0.0)

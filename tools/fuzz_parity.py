@@ -21,6 +21,8 @@ def gen(rs, binary):
     T = int(rs.choice([1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 40, 64, 100, 130, 257]))
     T = max(T, int(rs.randint(1, 4)))
     B = int(rs.choice([1, 2, 3, 5, 8, 13]))
+    if rs.uniform() < 0.04 and C <= 64:        # batches of more than one wave: the longest-first work queue
+        B, T, Lmax = int(rs.choice([1300, 3100, 4500])), min(T, 17), min(Lmax, 100)
     if C >= 512:
         T, B = min(T, 64), min(B, 3)
     hi = min(Lmax, T)
@@ -36,7 +38,7 @@ def gen(rs, binary):
     else:
         il = np.array([rs.randint(l, T + 1) for l in tl])
     tl, il = tl.astype(np.int64), il.astype(np.int64)
-    scale = float(rs.choice([1.0, 1.0, 4.0, 10.0]))
+    scale = float(rs.choice([1.0, 1.0, 4.0, 10.0] if binary else [1.0, 1.0, 4.0, 10.0, 40.0]))  # (multi-label: |x| > 100 is the documented BCE-clamp deviation)
     x = (rs.standard_normal((T, B, C)) * scale).astype(np.float32)
     peak = rs.choice(["none", "class", "path"])
     if binary:
