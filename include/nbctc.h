@@ -89,6 +89,9 @@ size_t nbctc_workspace_bytes(int64_t T, int64_t B, int64_t C, int64_t Lmax, int 
  * order (bit-reproducible; this is the scalar that is all-reduced across GPUs).
  * loss_reduced (nullable) receives (float)(weight_scalar * loss_sum), i.e. the reference's
  * return value torch.mean(loss) (NoBlankCTC.py:140) when weight_scalar = 1/B.
+ * Any finite float32 logits are inside the parity domain: the fused kernels work in the linear domain and hand the
+ * sequences whose emissions leave the float32 range (a label more than 83 nats under its row's maximum) to a
+ * log-domain kernel launched behind them on the same stream (results as for every other sequence, within 1e-5).
  */
 int nbctc_loss_grad_f32(const float* logits, int64_t T, int64_t B, int64_t C,
                         const int32_t* labels, int64_t Lmax,
