@@ -52,6 +52,7 @@ struct TiledWs {
   int64_t rec_bytes;
   int o_rec_ckx;
   int LW, NT, Lpad;
+  int rs32, es32;       // K12: B C and B Lmax, the row strides of logits and emission tile in floats (host gate: < 2^26)
 };
 
 struct Layout {
@@ -72,7 +73,7 @@ Layout layout(int64_t T, int64_t B, int64_t C, int64_t Lmax) {
   l.o_ckpt = take(sizeof(double) * (size_t)B * l.NT * l.Lpad);
   l.o_cke = take(sizeof(int) * (size_t)B * l.NT * 16);
   l.o_emis = take(sizeof(float) * (size_t)T * B * Lmax);
-  l.seq = Lmax <= 32 && T < (1 << 24);
+  l.seq = Lmax <= 32 && T < (1 << 24) && B * C < ((int64_t)1 << 26) && B * Lmax < ((int64_t)1 << 26);  // (32-bit row strides in the kernel)
   if (l.seq) {
     const size_t K = (size_t)((T + 3) / 4);
     l.o_rec_ckx = (int)align_up(sizeof(int) * (K / 2 + 1) * 32, 256);
@@ -305,7 +306,9 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   const int words = (__reduce_max_sync(kFull, n) + 4) >> 2;  // bytes 0..n
   const float k2 = stream::kLog2e / (float)C;
 
-  const int64_t rstride = p.B * p.C, estride = p.B * (int64_t)Lmax;
+  // row strides as 32-bit kernel arguments: used straight from the constant bank (the 64-bit products p.B * p.C were
+  // rebuilt in every tile: a fifth of the kernel's instructions went into addresses)
+  const int rstride = w.rs32, estride = w.es32;
   float* const e_b = w.emis + b * Lmax + lane;
   char* const rec = w.rec + b * w.rec_bytes;
   int* const cke = reinterpret_cast<int*>(rec) + lane;
@@ -322,15 +325,18 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   // one prefetch.global.L1 per tile requests the next tile's rows: lane = (row of the tile, 128-byte line of the row)
   const int LW = min((C * 4 + 127) / 128 + 1, 8);
   const int pf_ri = lane / LW;
-  const int pf_d = pf_ri * (int)rstride * 4 + min((lane - pf_ri * LW) * 128, C * 4 - 4) - 4 * lane;
+  const int pf_d = pf_ri * rstride * 4 + min((lane - pf_ri * LW) * 128, C * 4 - 4) - 4 * lane;
   const bool pf_lane = lane < kTT * LW;
-  for (int k = 0; k < K; ++k) {
-    const int nrow = min(kTT, Tb - k * kTT);
+  float* ep1 = e_b;  // the tile's first emission row
+  // one tile; F: all kTT rows are live (every tile but the sequence's last: no per-row predicates)
+  auto tile1 = [&](int k, auto full) {
+    constexpr bool F = decltype(full)::value;
+    const int nrow = F ? kTT : Tb - k * kTT;
     float v[NCI][kTT];
 #pragma unroll
     for (int r = 0; r < kTT; ++r) {
 #pragma unroll
-      for (int i = 0; i < NCI; ++i) v[i][r] = ((i + 1 < NCI || lane + 32 * i < C) && r < nrow) ? ldg_f(xr + 32 * i) : 0.f;
+      for (int i = 0; i < NCI; ++i) v[i][r] = ((i + 1 < NCI || lane + 32 * i < C) && (F || r < nrow)) ? ldg_f(xr + 32 * i) : 0.f;
       xr += rstride;
     }
     if (pf_lane && (k + 1) * kTT + pf_ri < Tb) pf_line_l1(reinterpret_cast<const char*>(xr) + pf_d);
@@ -380,11 +386,14 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
 #pragma unroll
     for (int r = 0; r < kTT; ++r) pe[r][0] = valid ? fmaxf(stream::ex2f((d[r] - sp[r]) * k2), stream::kPMin) : 0.f;
     if (want_grad && estore) {
-      float* e0 = e_b + (int64_t)k * kTT * estride;
+      float* e0 = ep1;
 #pragma unroll
-      for (int r = 0; r < kTT; ++r)
-        if (r < nrow) e0[r * estride] = pe[r][0];
+      for (int r = 0; r < kTT; ++r) {
+        if (F || r < nrow) *e0 = pe[r][0];
+        e0 += estride;
+      }
     }
+    ep1 += kTT * estride;
     __syncwarp();  // the staged rows are free for the next tile
     if (k > 0) {
       if ((k & 1) == 0) {
@@ -395,8 +404,11 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
     }
 #pragma unroll
     for (int r = 0; r < kTT; ++r)
-      if (r < nrow) alpha_step<1>(x, pe[r], fac);
-  }
+      if (F || r < nrow) alpha_step<1>(x, pe[r], fac);
+  };
+  const int Kf = Tb / kTT;  // full tiles
+  for (int k = 0; k < Kf; ++k) tile1(k, std::true_type{});
+  if (Kf < K) tile1(Kf, std::false_type{});
   // ---- read-out (NoBlankBinaryCTC.py:58-68)
   double zinv;
   int Ez;
@@ -425,11 +437,17 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   float pe_n[kTT];
   double xa_n;
   int ea_n;
-  auto fetch = [&](int k) {
-    const int nrow = min(kTT, Tb - k * kTT);
-    const float* e0 = e_b + (int64_t)k * kTT * estride;
+  float* ep2 = e_b + (int64_t)(K - 1) * kTT * estride;  // first emission row of the tile being fetched
+  auto fetch = [&](int k, auto full) {
+    constexpr bool F = decltype(full)::value;
+    const int nrow = F ? kTT : Tb - k * kTT;
+    const float* e0 = ep2;
 #pragma unroll
-    for (int r = 0; r < kTT; ++r) pe_n[r] = (r < nrow && estore) ? e0[r * estride] : 0.f;
+    for (int r = 0; r < kTT; ++r) {
+      pe_n[r] = ((F || r < nrow) && estore) ? *e0 : 0.f;
+      e0 += estride;
+    }
+    ep2 -= kTT * estride;
     ea_n = 0;
     if (k == 0) {
       xa_n = (lane & 1) ? -1.0 : 1.0;
@@ -438,16 +456,18 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
       if (k >= 2 && valid) ea_n = cke[(k >> 1) * 32];
     }
   };
-  fetch(K - 1);
-  for (int k = K - 1; k >= 0; --k) {
-    const int nrow = min(kTT, Tb - k * kTT);
-    float* e0 = e_b + (int64_t)k * kTT * estride;
+  if (Kf < K) fetch(K - 1, std::false_type{});
+  else fetch(K - 1, std::true_type{});
+  auto tile2 = [&](int k, auto full) {
+    constexpr bool F = decltype(full)::value;
+    const int nrow = F ? kTT : Tb - k * kTT;
+    float* eg = ep2 + (2 * kTT - 1) * estride;  // last row of this tile (ep2: the tile below it, fetched next)
     float pe[kTT][1];
 #pragma unroll
     for (int r = 0; r < kTT; ++r) pe[r][0] = pe_n[r];
     double xa[1] = {xa_n};
     const int ea = ea_n;
-    if (k > 0) fetch(k - 1);
+    if (k > 0) fetch(k - 1, std::true_type{});  // (only a sequence's last tile can be short)
     const int H = ea + eb - Ez;
     const int Ha = max(min(H, 0), -1000);
     const double ga = pow2z(Ha), gb = pow2z(H - Ha) * zinv;
@@ -456,23 +476,27 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
     double a[kTT];
 #pragma unroll
     for (int r = 0; r < kTT; ++r) {
-      if (r < nrow) alpha_step<1>(xa, pe[r], faca);
+      if (F || r < nrow) alpha_step<1>(xa, pe[r], faca);
       a[r] = xa[0] * ga;
     }
 #pragma unroll
     for (int r = kTT - 1; r >= 0; --r) {
-      if (r < nrow) {
+      if (F || r < nrow) {
         double bt[1];
         beta_step<1>(u, bt, pe[r], facb);
         const float g = (float)(a[r] * clamp_big(bt[0] * gb));
-        if (estore) e0[r * estride] = g;
+        if (estore) *eg = g;
       }
+      eg -= estride;
     }
-    if (++since == 2 || nrow < kTT) {
+    if (++since == 2 || (!F && nrow < kTT)) {
       since = 0;
       lane_rescale<1, false>(u, eb, facb, lane);
     }
-  }
+  };
+  int kd = K - 1;
+  if (Kf < K) tile2(kd--, std::false_type{});
+  for (; kd >= 0; --kd) tile2(kd, std::true_type{});
 }
 
 template <int NCI>
@@ -981,6 +1005,7 @@ int tiled_bin_launch(const Problem& p, void* ws, size_t ws_bytes, cudaStream_t s
   w.emis = reinterpret_cast<float*>(c + l.o_emis);
   w.LW = l.LW; w.NT = l.NT; w.Lpad = l.Lpad;
   w.rec = c + l.o_rec; w.rec_bytes = (int64_t)l.rec_bytes; w.o_rec_ckx = l.o_rec_ckx;
+  w.rs32 = (int)std::min<int64_t>(p.B * p.C, INT32_MAX); w.es32 = (int)std::min<int64_t>(p.B * p.Lmax, INT32_MAX);
   *flag_out = w.flag;
   // the flag and the class masks (set with atomicOr by the emission kernel) are contiguous: one memset
   NBCTC_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, l.o_cmask + sizeof(uint32_t) * (size_t)p.B * p.C * l.LW, stream));
