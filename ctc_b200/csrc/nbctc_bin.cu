@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kRowWarps * 32, NCI <= 5 ? 4 : 2) bin_emis_ker
 template <int NCI>
 __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
   using namespace sw;
-  constexpr int Cp = 32 * NCI + 8;  // row stride: rows start 8 banks apart
-  __shared__ float xs[kTT * Cp];
+  static_assert(kTT == 4, "a class's values of the tile's rows are one float4");
+  __shared__ float4 xs[32 * NCI];  // [class] -> the class's logits in the tile's 4 rows: one STS.128 / LDS.128 per class
   __shared__ __align__(16) uint32_t sl[32 * 8];
   const int lane = threadIdx.x;
   const int64_t b = blockIdx.x;
@@ -350,10 +350,10 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
       for (int i = 0; i < NCI; ++i) {
         const int c = lane + 32 * i;
         const bool in = i + 1 < NCI || c < C;
+        xs[c] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
 #pragma unroll
         for (int r = 0; r < kTT; ++r) {
           const float xv = v[i][r];
-          xs[r * Cp + c] = xv;
           const float f = 1.f + stream::ex2f(-fabsf(xv) * stream::kLog2e);
           pos[r] += in ? fmaxf(xv, 0.f) : 0.f;
           prod[r] *= in ? f : 1.f;
@@ -375,9 +375,8 @@ __global__ void __launch_bounds__(32, 28) bin_seq_kernel(Problem p, TiledWs w) {
           const int kk = wi * 4 + bb;
           if (kk == 0) continue;  // byte 0 is the count
           if (kk <= n) {
-            const float* col = xs + ((lw[wi] >> (8 * bb)) & 0xffu);
-#pragma unroll
-            for (int r = 0; r < kTT; ++r) d[r] += col[r * Cp];
+            const float4 q = xs[(lw[wi] >> (8 * bb)) & 0xffu];
+            d[0] += q.x; d[1] += q.y; d[2] += q.z; d[3] += q.w;
           }
         }
       }
