@@ -81,9 +81,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
 // flag[b] != 0 -> the sequence is redone; lse / ckx = scratch of the sequence (row log-partitions [T] float32, alpha
 // checkpoints [ceil(T/4)][Lpad] float64, Lpad = 32/64/128/256 by Lmax), strides in elements
 struct LogWs {
-  const int* flag;       // sequence b: flag_words (1 or 32, 16-byte aligned) ints at flag + b flag_stride, any non-zero = redo
-  int64_t flag_stride;
-  int flag_words;
+  const int* flag;       // [B] non-zero = redo the sequence
   float* lse_base;
   int64_t lse_stride;
   double* ckx_base;

@@ -4,8 +4,9 @@
 // with emissions p_t(s) = softmax(x_t)[label_s] held in float32 and floored at 2^-120: a label whose logit lies more
 // than 83 nats below its row's maximum cannot be represented, and a sequence whose admissible paths must pass through
 // such an emission would get a wrong loss and gradient.  Every fast kernel therefore raises flag[b] when it floors an
-// emission of a live state of sequence b, and this kernel -- launched after it on the same stream, one warp per
-// sequence, returning at once where the flag is clear -- redoes those sequences in the LOG domain, where a log-probability
+// emission of a live state of sequence b, and this kernel -- launched behind it on the same stream with programmatic
+// stream serialization; a small grid scans the flags, 8 per warp and step, and a warp that finds one set takes that
+// sequence -- redoes those sequences in the LOG domain, where a log-probability
 // of any size is just a number: float64 log alpha / log beta with a float32 correction term (logaddexp64, as the
 // generic path, NoBlankCTC.py:16-19 _logsumexp), alpha checkpoints every 4 steps in the workspace record of the
 // sequence, alpha replayed inside the tile next to beta, gamma = exp(log alpha + log beta - log Z).  It overwrites the
@@ -18,6 +19,7 @@ namespace nbctc {
 namespace {
 
 constexpr int kLogWarps = 4;
+constexpr int kScan = 8;  // flags looked at by one warp per step
 constexpr int kTT = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -33,25 +35,10 @@ __global__ void __launch_bounds__(kLogWarps * 32) logdom_kernel(Problem p, LogWs
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the fast kernel in front has finished and its stores are visible
   const int64_t nw = (int64_t)gridDim.x * kLogWarps;
-  for (int64_t b0 = ((int64_t)blockIdx.x * kLogWarps + warp) * 32; b0 < p.B; b0 += nw * 32) {
-    // 32 sequences per warp and step, one per lane
+  for (int64_t b0 = ((int64_t)blockIdx.x * kLogWarps + warp) * kScan; b0 < p.B; b0 += nw * kScan) {
+    // kScan sequences per warp and step (few, so that many flagged sequences spread over many warps)
     const int64_t bl = b0 + lane;
-    bool f = false;
-    if (bl < p.B) {
-      const int* q = w.flag + bl * w.flag_stride;
-      if (w.flag_words == 32) {  // one word per lane of the fast kernel: a 128-byte line
-        int4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = reinterpret_cast<const int4*>(q)[i];
-        int o = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o |= v[i].x | v[i].y | v[i].z | v[i].w;
-        f = o != 0;
-      } else {
-        f = q[0] != 0;
-      }
-    }
-    unsigned m = __ballot_sync(kFull, f);
+    unsigned m = __ballot_sync(kFull, lane < kScan && bl < p.B && w.flag[bl] != 0);
     while (m) {
       const int i = __ffs(m) - 1;
       m &= m - 1;
@@ -218,7 +205,7 @@ __device__ void logdom_sequence(const Problem& p, const LogWs& w, int64_t b, int
 }  // namespace
 
 int logdom_repair_launch(const Problem& p, const LogWs& w, cudaStream_t stream) {
-  const unsigned grid = (unsigned)std::min<int64_t>((p.B + kLogWarps * 32 - 1) / (kLogWarps * 32), 8 * 148);
+  const unsigned grid = (unsigned)std::min<int64_t>((p.B + kLogWarps * kScan - 1) / (kLogWarps * kScan), 8 * 148);
   // programmatic stream serialization: the launch overlaps the tail of the fast kernel in front (which signals
   // launch_dependents where it supports it; behind any other kernel this is an ordinary launch)
   cudaLaunchConfig_t cfg{};

@@ -169,7 +169,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
     }
     const int rcw = pl.NV == 4 ? launch_seqwide_nv<4>(W, pl.NS, grid, stream) : launch_seqwide_nv<8>(W, pl.NS, grid, stream);
     if (rcw != NBCTC_OK) return rcw;
-    LogWs lw{W.floor_flag, 1, 1, W.lse2, (int64_t)pl.Tp, W.ckx, (int64_t)pl.K * 32 * pl.NS};
+    LogWs lw{W.floor_flag, W.lse2, (int64_t)pl.Tp, W.ckx, (int64_t)pl.K * 32 * pl.NS};
     return logdom_repair_launch(p, lw, stream);
   }
   SwParams P{};
@@ -203,7 +203,7 @@ int seqwarp_launch(const Problem& p, void* ws, size_t ws_bytes, const float* row
   const int rcs = launch_seqwarp(P, pl.NS, pl.EPL, grid, stream);
   if (rcs != NBCTC_OK) return rcs;
   // sequences with an emission below the float32 floor: redone in the log domain, in their own records
-  LogWs lw{P.floor_flag, 1, 1, reinterpret_cast<float*>(P.rec), P.rec_bytes / 4, reinterpret_cast<double*>(P.rec + P.o_ckx), P.rec_bytes / 8};
+  LogWs lw{P.floor_flag, reinterpret_cast<float*>(P.rec), P.rec_bytes / 4, reinterpret_cast<double*>(P.rec + P.o_ckx), P.rec_bytes / 8};
   return logdom_repair_launch(p, lw, stream);
 }
 

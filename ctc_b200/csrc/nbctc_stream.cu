@@ -180,7 +180,7 @@ int fused_launch(const Problem& p, bool binary, void* ws, size_t ws_bytes, cudaS
   }
   if (rc != NBCTC_OK) return rc;
   // sequences with an emission below the float32 floor are redone in the log domain (nbctc_logdom.cu)
-  LogWs lw{pl.cfg.floor_flag, 1, 1, reinterpret_cast<float*>(w + l.o_rlse), p.T, reinterpret_cast<double*>(w + l.o_rckx), l.rK * pl.cfg.Lpad};
+  LogWs lw{pl.cfg.floor_flag, reinterpret_cast<float*>(w + l.o_rlse), p.T, reinterpret_cast<double*>(w + l.o_rckx), l.rK * pl.cfg.Lpad};
   return logdom_repair_launch(p, lw, stream);
 }
 

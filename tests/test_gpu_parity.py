@@ -561,7 +561,8 @@ def test_single_admissible_path_bctc(nb, case, flags):
 
 
 @pytest.mark.parametrize("flags", [8, 32], ids=["lockstep", "seqwarp"])
-@pytest.mark.parametrize("shape", [(64, 8, 157, 20), (50, 6, 157, 40), (40, 3, 512, 40), (70, 4, 64, 150), (33, 5, 1024, 256)],
+@pytest.mark.parametrize("shape", [(64, 8, 157, 20), (50, 6, 157, 40), (40, 3, 512, 40), (70, 4, 64, 150), (33, 5, 1024, 256),
+                                   (12, 301, 33, 9)],
                          ids=lambda s: "T%d_B%d_C%d_L%d" % s)
 def test_logit_gaps_beyond_the_float32_emission_floor(nb, shape, flags):
     """Logits whose label entries lie more than 83 nats under the row maximum: softmax(x)[label] is below 2^-120, which the
