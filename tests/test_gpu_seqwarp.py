@@ -189,6 +189,40 @@ def test_no_write_outside_the_caller_buffers(shape):
     _check(per, grad, x, lab, il, tl)
 
 
+@pytest.mark.parametrize("path", [8, SEQWARP], ids=["lockstep", "seqwarp"])
+@pytest.mark.parametrize("shape", [(37, 9, 157, 20), (23, 6, 33, 33), (30, 3, 1000, 200), (21, 70, 16, 150)],
+                         ids=lambda s: "T%d_B%d_C%d_L%d" % s)
+def test_repair_kernel_stays_inside_the_workspace(shape, path):
+    """The guard-region check with every second sequence beyond the float32 emission floor (logits times 40): the
+    log-domain repair kernel keeps its row log-partitions and checkpoints inside the workspace the query asked for."""
+    from ctc_b200 import _ffi
+    lib = _ffi.lib()
+    T, B, C, Lmax = shape
+    x, lab, il, tl = make_ctc_case(700 + T + C, T, B, C, Lmax)
+    x[:, 0::2] *= 40.0
+    xt = torch.tensor(x, device=DEV)
+    labt = torch.tensor(lab, device=DEV).int().contiguous()
+    ilt, tlt = torch.tensor(il, device=DEV), torch.tensor(tl, device=DEV)
+    flags = path | _ffi.FLAG_ALIGNED16
+    wsb = int(lib.nbctc_workspace_bytes(T, B, C, Lmax, 0, flags))
+    G = 4096
+    up = lambda n: (n + 255) // 256 * 256
+    n_grad, n_per, n_ws = up(T * B * C * 4), up(B * 4), up(wsb)
+    arena = torch.full((G + n_grad + G + n_per + G + n_ws + G,), 0x5A, dtype=torch.uint8, device=DEV)
+    o_grad, o_per, o_ws = G, G + n_grad + G, G + n_grad + G + n_per + G
+    base = arena.data_ptr()
+    rc = lib.nbctc_loss_grad_f32(xt.data_ptr(), T, B, C, labt.data_ptr(), Lmax, ilt.data_ptr(), tlt.data_ptr(), base + o_per, None, None,
+                                 base + o_grad, None, 1.0, base + o_ws, wsb, flags, torch.cuda.current_stream().cuda_stream)
+    _ffi.check(rc, "nbctc_loss_grad_f32")
+    torch.cuda.synchronize()
+    a = arena.cpu().numpy()
+    for lo, hi in ((0, G), (o_grad + T * B * C * 4, o_per), (o_per + B * 4, o_ws), (o_ws + wsb, len(a))):
+        assert np.all(a[lo:hi] == 0x5A), f"guard bytes [{lo},{hi}) were written"
+    grad = a[o_grad:o_grad + T * B * C * 4].view(np.float32).reshape(T, B, C).astype(np.float64)
+    per = a[o_per:o_per + B * 4].view(np.float32).astype(np.float64)
+    _check(per, grad, x, lab, il, tl)
+
+
 def test_misaligned_workspace_is_rejected():
     from ctc_b200 import _ffi
     lib = _ffi.lib()
